@@ -1,0 +1,176 @@
+/*
+ * genre_b200.h — C ABI of libgenre_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for the GenRe/ShapeHD geometric-projection hot path.  Every entry
+ * point takes plain device pointers, sizes, element strides and a cudaStream_t (passed as void*);
+ * there are no torch types.  The caller (the Python mirror of the reference's toolbox packages, or
+ * any other host) owns every buffer, including scratch ("workspace"): the library never allocates
+ * device memory and never synchronises the device.  All launches go to the given stream and are
+ * CUDA-graph capturable.
+ *
+ * Each function states the reference interface it replaces (paths relative to the reference root).
+ * Reference convention: cffi functions on THCudaTensor*, returning int 1, failing through
+ * THError("aborting") (toolbox/cam_bp/cam_bp/src/back_projection.c:9-57).  Here: return 0 on success,
+ * a positive cudaError_t if a launch failed, or a negative GENRE_B200_E* code for an argument error;
+ * genre_b200_last_error() gives the message (thread-local).  The Python mirror turns non-zero into
+ * RuntimeError, which is what THError became on the Python side.
+ *
+ * All tensors are fp32 unless stated otherwise.  "strides" are in ELEMENTS, not bytes, and may be 0
+ * (broadcast) where noted.
+ */
+#ifndef GENRE_B200_H
+#define GENRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENRE_B200_OK 0
+#define GENRE_B200_EINVAL (-1)      /* bad shape / null pointer / unsupported size        */
+#define GENRE_B200_EWORKSPACE (-2)  /* workspace too small (see *_workspace_bytes)         */
+#define GENRE_B200_EALIGN (-3)      /* a dense buffer is not 16-byte aligned               */
+
+/* flags for the projection entry points */
+#define GENRE_B200_FLAG_SHIFT_TDF 1u /* fuse Camera_back_projection_layer.shift_tdf: 1 - R*tdf */
+
+const char *genre_b200_last_error(void);
+/* library/ABI version: major*1000 + minor */
+int genre_b200_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera back-projection, depth -> voxel TDF.
+ * Replaces back_projection_forward (toolbox/cam_bp/cam_bp/src/back_projection.h:1,
+ * back_projection.c:9-17, back_projection_kernel.cu:199-306,760-838) together with the dense
+ * initialisation the Python caller performs (functions/cam_back_projection.py:22-24) and, when
+ * GENRE_B200_FLAG_SHIFT_TDF is set, modules/camera_backprojection_module.py:26-28.
+ *
+ *   depth   [N, C, H, W]  any strides (sN,sC,sH,sW); ray depth, pixels with depth < 0 are skipped
+ *   fl      [N, C]        strides (fN, fC)     focal length in pixels
+ *   camdist [N, C]        strides (dN, dC)     camera distance from the origin along -x
+ *   tdf     [N, C, R, R, R] dense, 16-byte aligned, written completely (no pre-initialisation needed)
+ *             without SHIFT: mean point-to-centre distance on hit voxels, 1/R elsewhere
+ *             with    SHIFT: 1 - R*mean on hit voxels, 1 - R*(1/R) elsewhere
+ *   cnt     [N, C, R, R, R] dense or NULL; if given, the per-voxel point count as fp32 (what the
+ *             reference keeps on ctx for backward, cam_back_projection.py:28)
+ *   workspace: genre_b200_voxelize_workspace_bytes(N*C, H*W, R) bytes, 16-byte aligned
+ * ------------------------------------------------------------------------------------------- */
+size_t genre_b200_voxelize_workspace_bytes(int64_t n_maps, int64_t pixels_per_map, int res);
+
+int genre_b200_cam_bp_forward(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W,
+                              int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                              const float *fl, int64_t fN, int64_t fC,
+                              const float *camdist, int64_t dN, int64_t dC,
+                              float *tdf, float *cnt, int res, unsigned flags,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces back_projection_backward (back_projection.h:2, back_projection_kernel.cu:365-471,897-963)
+ * with the intended cam_dist indexing (the reference reads cam_dist with cnt's strides at :401).
+ *   cnt, grad_tdf [N,C,R,R,R] dense;  grad_depth [N,C,H,W] dense (fully written);
+ *   grad_fl, grad_camdist [N,C] dense (fully written). */
+int genre_b200_cam_bp_backward(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W,
+                               int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                               const float *fl, int64_t fN, int64_t fC,
+                               const float *camdist, int64_t dN, int64_t dC,
+                               const float *cnt, const float *grad_tdf, int res,
+                               float *grad_depth, float *grad_fl, float *grad_camdist, void *stream);
+
+/* Replaces get_surface_mask (back_projection.h:3, back_projection_kernel.cu:309-358,840-891).
+ *   cnt  [N,C,R,R,R] dense (from genre_b200_cam_bp_forward);  mask [N,C,R,R,R] dense, fully written:
+ *   1 everywhere except empty voxels that lie behind the observed depth surface. */
+int genre_b200_surface_mask(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W,
+                            int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                            const float *fl, int64_t fN, int64_t fC,
+                            const float *camdist, int64_t dN, int64_t dC,
+                            const float *cnt, float *mask, int res, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spherical back-projection, spherical depth map -> voxel TDF + count.
+ * Replaces spherical_back_proj_forward / _backward (back_projection.h:4-5,
+ * back_projection_kernel.cu:474-757; functions/sperical_to_tdf.py:13-47).
+ *   sph  [N, C, H, W]    any strides; radius along the ray, < 0 skipped
+ *   grid [N, C, H, W, 3] any strides (gN may be 0: one direction table shared by the batch)
+ *   tdf, cnt [N,C,R,R,R] dense, fully written: mean distance / count on hit voxels, 0 elsewhere
+ * ------------------------------------------------------------------------------------------- */
+int genre_b200_sph_bp_forward(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W,
+                              int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                              const float *grid, int64_t gN, int64_t gC, int64_t gH, int64_t gW, int64_t gD,
+                              float *tdf, float *cnt, int res,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+int genre_b200_sph_bp_backward(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W,
+                               int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                               const float *grid, int64_t gN, int64_t gC, int64_t gH, int64_t gW, int64_t gD,
+                               const float *cnt, const float *grad_tdf, int res,
+                               float *grad_sph, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stop probability along rays.  Replaces calc_prob_forward / calc_prob_backward
+ * (toolbox/calc_prob/calc_prob/src/calc_prob.h:1-2, calc_prob_kernel.cu:112-266).
+ *   prob_in, stop_prob, grad_in...: [n_rays, Z] dense (the reference's [N,C,X,Y,Z] flattened)
+ *   forward : stop[z] = p[z] * prod_{k<z} (1 - p[k])        (p must lie in (0,1), as the reference)
+ *   backward: grad_prob from stop_prob_weighted = stop * grad_stop (calc_prob.py:27)
+ * ------------------------------------------------------------------------------------------- */
+int genre_b200_calc_prob_forward(const float *prob_in, float *stop_prob, int64_t n_rays, int64_t Z, void *stream);
+int genre_b200_calc_prob_backward(const float *prob_in, const float *stop_prob_weighted, float *grad_prob,
+                                  int64_t n_rays, int64_t Z, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused spherical renderer: voxel occupancy -> spherical depth map.
+ * Replaces render_spherical.forward (toolbox/spherical_proj.py:62-72): trilinear grid_sample
+ * (align_corners=True semantics of torch 0.4.1, zero padding) of vox.permute(0,1,4,3,2) along
+ * rays dir[h,w]*2*(1 - k/(Z-1)), clamp to [1e-5, 1-1e-5], stop-probability scan, expected depth
+ * sum_k s_k*k/(Z-1) + prod_k(1 - p_k), without materialising any [N,1,S,S,Z] tensor.
+ *   vox  [N, R, R, R] dense (C must be 1 as in the reference)
+ *   dirs [S, S, 3]    dense fp64 unit directions (the numpy table of spherical_proj.py:43-51 BEFORE its
+ *                     float cast; sample positions are formed in fp64 and rounded once, like :52-57)
+ *   depth_weight [Z]  the module's registered buffer linspace(0,1,Z) (spherical_proj.py:58)
+ *   out  [N, S, S]    dense
+ * ------------------------------------------------------------------------------------------- */
+int genre_b200_render_spherical_forward(const float *vox, int64_t N, int res,
+                                        const double *dirs, int sph_res, int z_res,
+                                        const float *depth_weight, float *out, void *stream);
+/* gradient of the above w.r.t. vox; grad_vox [N,R,R,R] must be zeroed by the caller (accumulated with
+ * atomics, like grid_sampler_3d_backward); z_res <= 256 */
+int genre_b200_render_spherical_backward(const float *vox, int64_t N, int res,
+                                         const double *dirs, int sph_res, int z_res,
+                                         const float *depth_weight,
+                                         const float *grad_out, float *grad_vox, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer nearest-neighbour distance.  Replaces nnd_forward_cuda / nnd_backward_cuda
+ * (toolbox/nndistance/src/my_lib_cuda.h:1-4, nnd_cuda.cu:6-177; functions/nnd.py:8-63).
+ *   xyz1 [B,N,3], xyz2 [B,M,3] dense;  dist1 [B,N], dist2 [B,M] squared distances;
+ *   idx1 [B,N], idx2 [B,M] int32 argmin, lowest index on ties.
+ *   backward fully writes grad_xyz1 [B,N,3], grad_xyz2 [B,M,3] (zeroing included).
+ * Unlike the reference (nnd_cuda.cu:130-131 launches on the legacy default stream) the given
+ * stream is honoured.
+ * ------------------------------------------------------------------------------------------- */
+int genre_b200_nnd_forward(const float *xyz1, const float *xyz2, int64_t B, int64_t N, int64_t M,
+                           float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, void *stream);
+int genre_b200_nnd_backward(const float *xyz1, const float *xyz2, int64_t B, int64_t N, int64_t M,
+                            const float *grad_dist1, const float *grad_dist2,
+                            const int32_t *idx1, const int32_t *idx2,
+                            float *grad_xyz1, float *grad_xyz2, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage-level entry points of the voxelisation pipeline (used by bench.py to time the dominant
+ * kernel on its own, and by tests).  genre_b200_cam_bp_forward == project + bin + splat.
+ * ------------------------------------------------------------------------------------------- */
+int genre_b200_cam_bp_stage_project(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W,
+                                    int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                                    const float *fl, int64_t fN, int64_t fC,
+                                    const float *camdist, int64_t dN, int64_t dC, int res,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+int genre_b200_voxelize_stage_bin(int64_t n_maps, int64_t pixels_per_map, int res,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int genre_b200_voxelize_stage_splat(int64_t n_maps, int64_t pixels_per_map, int res,
+                                    float *tdf, float *cnt, float hit_alpha, float hit_beta, float background,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENRE_B200_H */
