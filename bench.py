@@ -48,7 +48,7 @@ def config(args, n_gpus):
     return {"workload": "cam_bp 256x256 depth -> 128^3 voxel back-projection, batch=%d per GPU (BASELINE configs[1])" % args.batch,
             "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "depth_hw": [H, W], "voxel_res": RES,
             "fl": FL, "cam_dist": CAM_DIST, "shift_tdf": True, "parallelism": "replicas x%d (batch-sharded, no collective)" % n_gpus,
-            "l2": "no explicit flush: each step streams 256 MiB of output + 42 MB of scratch (> 126 MB L2); inputs rotate over 4 buffers"}
+            "l2": "no explicit flush: each step streams 256 MiB of output + ~13 MB of scratch (> 126 MB L2); inputs rotate over 4 buffers"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -199,7 +199,7 @@ def run_b200(args):
     graphs = []
     with torch.no_grad():
         if use_graph:
-            # one CUDA graph per rotating input buffer (project + bin + splat + counter memset, 3 kernels)
+            # one CUDA graph per rotating input buffer (counter memset + project + splat: 2 kernels)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -236,7 +236,7 @@ def run_b200(args):
         t_wall1 = time.time()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-        launches = (K * 3) if use_graph else (_lib.launch_count - launches0)
+        launches = (K * 2) if use_graph else (_lib.launch_count - launches0)
 
     value = world * B * K / (ms_total * 1e-3)
 
@@ -276,7 +276,6 @@ def run_b200(args):
         cd = torch.full((1, 1), CAM_DIST, device=dev).expand(B, 1)
         _lib.call("genre_b200_cam_bp_stage_project", x.data_ptr(), B, 1, H, W, *x.stride(), fl.data_ptr(), *fl.stride(),
                   cd.data_ptr(), *cd.stride(), RES, ws.data_ptr(), nbytes, st)
-        _lib.call("genre_b200_voxelize_stage_bin", B, H * W, RES, ws.data_ptr(), nbytes, st)
 
         def splat():
             _lib.call("genre_b200_voxelize_stage_splat", B, H * W, RES, tdf.data_ptr(), None, 1.0, -1.0 / 16777216.0, 0.0,
@@ -308,7 +307,7 @@ def run_b200(args):
             except Exception:
                 pass
         achieved = alg_bytes / (splat_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "vox_splat_kernel<true,false>", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "vox_splat_kernel<VEC=true,WRITE_CNT=false>", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": splat_ms * 1e3,
                     "whole_op_GBps": alg_bytes / (ms_total / K * 1e-3) / 1e9,

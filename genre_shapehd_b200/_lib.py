@@ -36,7 +36,6 @@ _SIGNATURES = {
     "genre_b200_nnd_backward": [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "genre_b200_cam_bp_stage_project": [_ptr] + [_i64] * 8 + [_ptr, _i64, _i64, _ptr, _i64, _i64, _int, _ptr, _size,
                                                              _ptr],
-    "genre_b200_voxelize_stage_bin": [_i64, _i64, _int, _ptr, _size, _ptr],
     "genre_b200_voxelize_stage_splat": [_i64, _i64, _int, _ptr, _ptr, _f32, _f32, _f32, _ptr, _size, _ptr],
 }
 
@@ -49,11 +48,11 @@ launch_count = 0  # kernels of this library enqueued through the binding (bench.
 
 # how many of this library's KERNELS one call of each entry point launches (memset nodes not counted)
 _LAUNCHES = {
-    "genre_b200_cam_bp_forward": 3, "genre_b200_cam_bp_backward": 1, "genre_b200_surface_mask": 1,
-    "genre_b200_sph_bp_forward": 3, "genre_b200_sph_bp_backward": 1, "genre_b200_calc_prob_forward": 1,
+    "genre_b200_cam_bp_forward": 2, "genre_b200_cam_bp_backward": 1, "genre_b200_surface_mask": 1,
+    "genre_b200_sph_bp_forward": 2, "genre_b200_sph_bp_backward": 1, "genre_b200_calc_prob_forward": 1,
     "genre_b200_calc_prob_backward": 1, "genre_b200_render_spherical_forward": 1,
     "genre_b200_render_spherical_backward": 1, "genre_b200_nnd_forward": 1, "genre_b200_nnd_backward": 1,
-    "genre_b200_cam_bp_stage_project": 1, "genre_b200_voxelize_stage_bin": 1, "genre_b200_voxelize_stage_splat": 1,
+    "genre_b200_cam_bp_stage_project": 1, "genre_b200_voxelize_stage_splat": 1,
 }
 
 

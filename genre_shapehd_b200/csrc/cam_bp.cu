@@ -31,8 +31,8 @@ struct CamPoint {
 };
 
 // shared by forward and backward: pixel (h, w) with ray depth d -> point and voxel index
-__device__ __forceinline__ CamPoint cam_unproject(float d, float fl, float cam_dist, int h, int w, float Hm1,
-                                                  float Wm1, int R, float Rf) {
+__device__ __forceinline__ CamPoint cam_unproject(float d, float fl, const ExactDivisor &dfl, float cam_dist, int h,
+                                                  int w, float Hm1, float Wm1, int R, float Rf) {
   CamPoint p;
   p.imh = __fmaf_rn(Hm1, -0.5f, (float)h);
   p.imw = __fmaf_rn(Wm1, -0.5f, (float)w);
@@ -40,8 +40,8 @@ __device__ __forceinline__ CamPoint cam_unproject(float d, float fl, float cam_d
   p.norm = __fsqrt_rn(n2);
   const float cos_theta = __fdiv_rn(fl, p.norm);
   const float z = __fmul_rn(d, cos_theta);
-  p.gy = __fdiv_rn(__fmul_rn(p.imw, -z), fl);
-  p.gz = __fdiv_rn(__fmul_rn(p.imh, -z), fl);
+  p.gy = div_exact(__fmul_rn(p.imw, -z), dfl);
+  p.gz = div_exact(__fmul_rn(p.imh, -z), dfl);
   p.gx = __fadd_rn(z, -cam_dist);
   p.ix = floor_i_ref(__fmul_rn(__fadd_rn(p.gx, 0.5f), Rf));
   p.iy = floor_i_ref(__fmul_rn(__fadd_rn(p.gy, 0.5f), Rf));
@@ -51,50 +51,73 @@ __device__ __forceinline__ CamPoint cam_unproject(float d, float fl, float cam_d
 }
 
 // ------------------------------------------------------------------------------------------------
-// project: one thread per pixel
+// project: PROJ_PIX pixels per thread (independent loads and tickets in flight), 1024 pixels per CTA
 // ------------------------------------------------------------------------------------------------
 constexpr int PROJ_THREADS = 256;
+constexpr int PROJ_PIX = 4;
 
 template <bool W_FAST>
 __global__ void __launch_bounds__(PROJ_THREADS)
 cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long long sN, long long sC, long long sH,
                    long long sW, const float *__restrict__ fl_in, long long fN, long long fC,
-                   const float *__restrict__ cd_in, long long dN, long long dC, int R, float qscale,
-                   unsigned *__restrict__ counts, unsigned *__restrict__ pix_gv, unsigned *__restrict__ pix_q,
-                   unsigned *__restrict__ pix_rank, int ntiles) {
+                   const float *__restrict__ cd_in, long long dN, long long dC, int R, float qscale, VoxWorkspace ws,
+                   int fast_shift) {
+  extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
   const int map = blockIdx.y;
   const int n = map / C, c = map - n * C;
   const int P = H * W;
-  const int p = blockIdx.x * PROJ_THREADS + threadIdx.x;
-  unsigned gv = VOX_INVALID, q = 0;
-  if (p < P) {
-    int h, w;
-    if (W_FAST) { h = p / W; w = p - h * W; } else { w = p / H; h = p - w * H; }
-    const float d = depth[n * sN + c * sC + h * sH + w * sW];
-    if (!(d < 0.0f)) {  // reference skips only d < 0 (background is 0 in GenRe and falls out of bounds)
-      const float fl = fl_in[n * fN + c * fC];
-      const float cam_dist = cd_in[n * dN + c * dC];
-      const float Rf = (float)R;
-      const CamPoint pt = cam_unproject(d, fl, cam_dist, h, w, __fadd_rn((float)H, -1.0f),
-                                        __fadd_rn((float)W, -1.0f), R, Rf);
+  const float *dmap = depth + n * sN + c * sC;
+  const float fl = fl_in[n * fN + c * fC];
+  const float cam_dist = cd_in[n * dN + c * dC];
+  const ExactDivisor dfl = make_divisor(fl);
+  const VoxGrid grid = make_grid(R);
+  const float Hm1 = __fadd_rn((float)H, -1.0f), Wm1 = __fadd_rn((float)W, -1.0f);
+  const int fast = W_FAST ? W : H;  // extent of the axis consecutive threads walk along
+
+  // A pixel with depth exactly 0 (GenRe's background, depth_pred_with_sph_inpaint.py:139) unprojects to
+  // (-cam_dist, -+0, -+0) whatever its position: z = 0 * cos = 0, gy = (w~ * -0) / fl = -+0.  Whether that point is
+  // inside the grid is therefore a property of the map, evaluated once with the same operations; when it is
+  // outside (any camera further than 0.5 from the origin) such pixels skip the whole unprojection.
+  bool zero_in_bounds;
+  {
+    const int ix0 = floor_i_ref(__fmul_rn(__fadd_rn(__fadd_rn(0.0f, -cam_dist), 0.5f), grid.Rf));
+    const int iyz0 = floor_i_ref(__fmul_rn(0.5f, grid.Rf));
+    zero_in_bounds = (ix0 >= 0) & (ix0 < R) & (iyz0 >= 0) & (iyz0 < R);
+    const float afl = fabsf(fl);
+    if (!(afl >= 0x1p-40f && afl <= 0x1p40f)) zero_in_bounds = true;  // degenerate focal length: no shortcut
+  }
+
+  const int p0 = blockIdx.x * (PROJ_THREADS * PROJ_PIX) + threadIdx.x;
+  float d[PROJ_PIX];
+  int hh[PROJ_PIX], ww[PROJ_PIX];
+#pragma unroll
+  for (int k = 0; k < PROJ_PIX; ++k) {
+    const int p = p0 + k * PROJ_THREADS;
+    const int slow = fast_shift >= 0 ? (p >> fast_shift) : (p / fast);
+    const int fst = p - slow * fast;
+    hh[k] = W_FAST ? slow : fst;
+    ww[k] = W_FAST ? fst : slow;
+    d[k] = (p < P) ? dmap[hh[k] * sH + ww[k] * sW] : -1.0f;
+  }
+  unsigned gv[PROJ_PIX], q[PROJ_PIX];
+#pragma unroll
+  for (int k = 0; k < PROJ_PIX; ++k) {
+    gv[k] = VOX_INVALID;
+    q[k] = 0;
+    // reference skips only d < 0 (back_projection_kernel.cu:225)
+    if (!(d[k] < 0.0f) && (zero_in_bounds || d[k] != 0.0f)) {
+      const CamPoint pt = cam_unproject(d[k], fl, dfl, cam_dist, hh[k], ww[k], Hm1, Wm1, R, grid.Rf);
       if (pt.in_bounds) {
-        const float cx = __fadd_rn(__fdiv_rn(__fadd_rn((float)pt.ix, 0.5f), Rf), -0.5f);
-        const float cy = __fadd_rn(__fdiv_rn(__fadd_rn((float)pt.iy, 0.5f), Rf), -0.5f);
-        const float cz = __fadd_rn(__fdiv_rn(__fadd_rn((float)pt.iz, 0.5f), Rf), -0.5f);
-        const float dx = __fadd_rn(pt.gx, -cx), dy = __fadd_rn(pt.gy, -cy), dz = __fadd_rn(pt.gz, -cz);
+        const float dx = __fadd_rn(pt.gx, -vox_centre(pt.ix, grid));
+        const float dy = __fadd_rn(pt.gy, -vox_centre(pt.iy, grid));
+        const float dz = __fadd_rn(pt.gz, -vox_centre(pt.iz, grid));
         const float dist = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
-        gv = (unsigned)((pt.ix * R + pt.iy) * R + pt.iz);
-        q = vox_quantise(dist, qscale);
+        gv[k] = (unsigned)((pt.ix * R + pt.iy) * R + pt.iz);
+        q[k] = vox_quantise(dist, qscale);
       }
     }
   }
-  const unsigned rank = vox_take_ticket(gv, counts + (size_t)map * ntiles);
-  if (p < P) {
-    const size_t o = (size_t)map * P + p;
-    pix_gv[o] = gv;
-    pix_q[o] = q;
-    pix_rank[o] = rank;
-  }
+  vox_emit<PROJ_PIX, PROJ_THREADS>(gv, q, map, ws, P, s_hist);
 }
 
 static int cam_check(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W, const float *fl,
@@ -106,21 +129,28 @@ static int cam_check(const float *depth, int64_t N, int64_t C, int64_t H, int64_
   return vox_check_common(N * C, H * W, res);
 }
 
+static inline int log2_exact(int64_t v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1ll << s) < v) ++s;
+  return s;
+}
+
 static int cam_project_launch(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN, int64_t sC,
                               int64_t sH, int64_t sW, const float *fl, int64_t fN, int64_t fC, const float *camdist,
                               int64_t dN, int64_t dC, int res, const VoxWorkspace &w, cudaStream_t st) {
   const int64_t P = H * W;
-  dim3 grid((unsigned)((P + PROJ_THREADS - 1) / PROJ_THREADS), (unsigned)(N * C));
+  const int per_cta = PROJ_THREADS * PROJ_PIX;
+  dim3 grid((unsigned)((P + per_cta - 1) / per_cta), (unsigned)(N * C));
   const float qscale = (float)res * 16777216.0f;
   const bool w_fast = llabs(sW) <= llabs(sH);  // map consecutive threads to the denser image axis
+  const size_t smem = (size_t)w.ntiles * 4;
   if (w_fast)
-    cam_project_kernel<true><<<grid, PROJ_THREADS, 0, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, sH, sW, fl, fN, fC,
-                                                           camdist, dN, dC, res, qscale, w.counts, w.pix_gv, w.pix_q,
-                                                           w.pix_rank, w.ntiles);
+    cam_project_kernel<true><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, sH, sW, fl, fN,
+                                                              fC, camdist, dN, dC, res, qscale, w, log2_exact(W));
   else
-    cam_project_kernel<false><<<grid, PROJ_THREADS, 0, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, sH, sW, fl, fN,
-                                                            fC, camdist, dN, dC, res, qscale, w.counts, w.pix_gv,
-                                                            w.pix_q, w.pix_rank, w.ntiles);
+    cam_project_kernel<false><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, sH, sW, fl, fN,
+                                                               fC, camdist, dN, dC, res, qscale, w, log2_exact(H));
   return check_launch("cam_bp project kernel");
 }
 
@@ -148,7 +178,7 @@ cam_bp_backward_kernel(const float *__restrict__ depth, int C, int H, int W, lon
       const float fl = fl_in[n * fN + c * fC];
       const float cam_dist = cd_in[n * dN + c * dC];
       const float Rf = (float)R;
-      const CamPoint pt = cam_unproject(d, fl, cam_dist, h, w, __fadd_rn((float)H, -1.0f),
+      const CamPoint pt = cam_unproject(d, fl, make_divisor(fl), cam_dist, h, w, __fadd_rn((float)H, -1.0f),
                                         __fadd_rn((float)W, -1.0f), R, Rf);
       if (pt.in_bounds) {
         // voxel centre: the reference's backward evaluates this in double (literals 0.5), :428-430
@@ -289,9 +319,6 @@ extern "C" int genre_b200_cam_bp_forward(const float *depth, int64_t N, int64_t 
   GB_REQUIRE(vox_carve(workspace, workspace_bytes, N * C, H * W, res, &w), GENRE_B200_EWORKSPACE,
              "cam_bp: workspace too small or misaligned (need %zu bytes)", vox_workspace_bytes(N * C, H * W, res));
   cudaStream_t st = as_stream(stream);
-  if (int rc = vox_clear_counts(w, N * C, st)) return rc;
-  if (int rc = cam_project_launch(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, st)) return rc;
-  if (int rc = vox_bin(w, N * C, H * W, st)) return rc;
   // sum_q / count is the mean distance in units of 2^-24 voxel edges.
   //   raw  : tdf = mean               , background 1/R (cam_back_projection.py:23-24 + kernel bias :304,:829)
   //   shift: tdf = 1 - R * mean       , background 1 - R * (1/R)   (camera_backprojection_module.py:26-28)
@@ -306,6 +333,8 @@ extern "C" int genre_b200_cam_bp_forward(const float *depth, int64_t N, int64_t 
     beta = (float)((1.0 / 16777216.0) / (double)res);
     bg = inv_r;
   }
+  if (int rc = vox_clear_counts(w, N * C, st)) return rc;
+  if (int rc = cam_project_launch(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, st)) return rc;
   return vox_splat(w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st);
 }
 

@@ -29,44 +29,56 @@ __device__ __forceinline__ SphPoint sph_unproject(float r, float dxg, float dyg,
   return p;
 }
 
+constexpr int SPH_PIX = 4;  // pixels per thread in the project stage
+
 template <bool W_FAST>
 __global__ void __launch_bounds__(SPH_THREADS)
 sph_project_kernel(const float *__restrict__ sph, int C, int H, int W, long long sN, long long sC, long long sH,
                    long long sW, const float *__restrict__ grid, long long gN, long long gC, long long gH,
-                   long long gW, long long gD, int R, float qscale, unsigned *__restrict__ counts,
-                   unsigned *__restrict__ pix_gv, unsigned *__restrict__ pix_q, unsigned *__restrict__ pix_rank,
-                   int ntiles) {
+                   long long gW, long long gD, int R, float qscale, VoxWorkspace ws) {
+  extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
   const int map = blockIdx.y;
   const int n = map / C, c = map - n * C;
   const int P = H * W;
-  const int p = blockIdx.x * SPH_THREADS + threadIdx.x;
-  unsigned gv = VOX_INVALID, q = 0;
-  if (p < P) {
-    int h, w;
-    if (W_FAST) { h = p / W; w = p - h * W; } else { w = p / H; h = p - w * H; }
-    const float r = sph[n * sN + c * sC + h * sH + w * sW];
-    if (!(r < 0.0f)) {
-      const float *g = grid + n * gN + c * gC + h * gH + w * gW;
-      const float Rf = (float)R;
-      const SphPoint pt = sph_unproject(r, g[0], g[gD], g[2 * gD], R, Rf);
+  const float *smap = sph + n * sN + c * sC;
+  const float *gmap = grid + n * gN + c * gC;
+  const VoxGrid vg = make_grid(R);
+  const int fast = W_FAST ? W : H;
+  const int p0 = blockIdx.x * (SPH_THREADS * SPH_PIX) + threadIdx.x;
+  float r[SPH_PIX], dxg[SPH_PIX], dyg[SPH_PIX], dzg[SPH_PIX];
+#pragma unroll
+  for (int k = 0; k < SPH_PIX; ++k) {
+    const int p = p0 + k * SPH_THREADS;
+    const int slow = p / fast, fst = p - slow * fast;
+    const int h = W_FAST ? slow : fst, w = W_FAST ? fst : slow;
+    r[k] = -1.0f;
+    dxg[k] = dyg[k] = dzg[k] = 0.0f;
+    if (p < P) {
+      r[k] = smap[h * sH + w * sW];
+      const float *g = gmap + h * gH + w * gW;
+      dxg[k] = g[0];
+      dyg[k] = g[gD];
+      dzg[k] = g[2 * gD];
+    }
+  }
+  unsigned gv[SPH_PIX], q[SPH_PIX];
+#pragma unroll
+  for (int k = 0; k < SPH_PIX; ++k) {
+    gv[k] = VOX_INVALID;
+    q[k] = 0;
+    if (!(r[k] < 0.0f)) {
+      const SphPoint pt = sph_unproject(r[k], dxg[k], dyg[k], dzg[k], R, vg.Rf);
       if (pt.in_bounds) {
-        const float cx = __fadd_rn(__fdiv_rn(__fadd_rn((float)pt.ix, 0.5f), Rf), -0.5f);
-        const float cy = __fadd_rn(__fdiv_rn(__fadd_rn((float)pt.iy, 0.5f), Rf), -0.5f);
-        const float cz = __fadd_rn(__fdiv_rn(__fadd_rn((float)pt.iz, 0.5f), Rf), -0.5f);
-        const float dx = __fadd_rn(pt.gx, -cx), dy = __fadd_rn(pt.gy, -cy), dz = __fadd_rn(pt.gz, -cz);
+        const float dx = __fadd_rn(pt.gx, -vox_centre(pt.ix, vg));
+        const float dy = __fadd_rn(pt.gy, -vox_centre(pt.iy, vg));
+        const float dz = __fadd_rn(pt.gz, -vox_centre(pt.iz, vg));
         const float dist = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
-        gv = (unsigned)((pt.ix * R + pt.iy) * R + pt.iz);
-        q = vox_quantise(dist, qscale);
+        gv[k] = (unsigned)((pt.ix * R + pt.iy) * R + pt.iz);
+        q[k] = vox_quantise(dist, qscale);
       }
     }
   }
-  const unsigned rank = vox_take_ticket(gv, counts + (size_t)map * ntiles);
-  if (p < P) {
-    const size_t o = (size_t)map * P + p;
-    pix_gv[o] = gv;
-    pix_q[o] = q;
-    pix_rank[o] = rank;
-  }
+  vox_emit<SPH_PIX, SPH_THREADS>(gv, q, map, ws, P, s_hist);
 }
 
 __global__ void __launch_bounds__(SPH_THREADS)
@@ -129,20 +141,18 @@ extern "C" int genre_b200_sph_bp_forward(const float *sph, int64_t N, int64_t C,
   GB_REQUIRE(vox_carve(workspace, workspace_bytes, N * C, H * W, res, &w), GENRE_B200_EWORKSPACE,
              "sph_bp: workspace too small or misaligned (need %zu bytes)", vox_workspace_bytes(N * C, H * W, res));
   cudaStream_t st = as_stream(stream);
-  if (int rc = vox_clear_counts(w, N * C, st)) return rc;
   const int64_t P = H * W;
-  dim3 grd((unsigned)((P + SPH_THREADS - 1) / SPH_THREADS), (unsigned)(N * C));
   const float qscale = (float)res * 16777216.0f;
+  if (int rc = vox_clear_counts(w, N * C, st)) return rc;
+  dim3 grd((unsigned)((P + SPH_THREADS * SPH_PIX - 1) / (SPH_THREADS * SPH_PIX)), (unsigned)(N * C));
+  const size_t smem = (size_t)w.ntiles * 4;
   if (llabs(sW) <= llabs(sH))
-    sph_project_kernel<true><<<grd, SPH_THREADS, 0, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN, gC, gH,
-                                                         gW, gD, res, qscale, w.counts, w.pix_gv, w.pix_q, w.pix_rank,
-                                                         w.ntiles);
+    sph_project_kernel<true><<<grd, SPH_THREADS, smem, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN, gC,
+                                                            gH, gW, gD, res, qscale, w);
   else
-    sph_project_kernel<false><<<grd, SPH_THREADS, 0, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN, gC,
-                                                          gH, gW, gD, res, qscale, w.counts, w.pix_gv, w.pix_q,
-                                                          w.pix_rank, w.ntiles);
+    sph_project_kernel<false><<<grd, SPH_THREADS, smem, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN,
+                                                             gC, gH, gW, gD, res, qscale, w);
   if (int rc = check_launch("sph_bp project kernel")) return rc;
-  if (int rc = vox_bin(w, N * C, P, st)) return rc;
   // tdf = mean distance on hit voxels, 0 elsewhere (sperical_to_tdf.py:26-27 zero init, kernel bias 0 at :695)
   const float beta = (float)((1.0 / 16777216.0) / (double)res);
   return vox_splat(w, N * C, P, res, tdf, cnt, 0.0f, beta, 0.0f, st);

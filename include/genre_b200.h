@@ -157,15 +157,13 @@ int genre_b200_nnd_backward(const float *xyz1, const float *xyz2, int64_t B, int
 
 /* ---------------------------------------------------------------------------------------------
  * Stage-level entry points of the voxelisation pipeline (used by bench.py to time the dominant
- * kernel on its own, and by tests).  genre_b200_cam_bp_forward == project + bin + splat.
+ * kernel on its own, and by tests).  genre_b200_cam_bp_forward == stage_project + stage_splat.
  * ------------------------------------------------------------------------------------------- */
 int genre_b200_cam_bp_stage_project(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W,
                                     int64_t sN, int64_t sC, int64_t sH, int64_t sW,
                                     const float *fl, int64_t fN, int64_t fC,
                                     const float *camdist, int64_t dN, int64_t dC, int res,
                                     void *workspace, size_t workspace_bytes, void *stream);
-int genre_b200_voxelize_stage_bin(int64_t n_maps, int64_t pixels_per_map, int res,
-                                  void *workspace, size_t workspace_bytes, void *stream);
 int genre_b200_voxelize_stage_splat(int64_t n_maps, int64_t pixels_per_map, int res,
                                     float *tdf, float *cnt, float hit_alpha, float hit_beta, float background,
                                     void *workspace, size_t workspace_bytes, void *stream);
