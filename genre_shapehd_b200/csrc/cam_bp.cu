@@ -56,15 +56,19 @@ __device__ __forceinline__ CamPoint cam_unproject(float d, float fl, const Exact
 constexpr int PROJ_THREADS = 256;
 constexpr int PROJ_PIX = 4;
 
+// Offsets inside one depth map are 32-bit (checked on the host); only the per-map base is 64-bit.
 template <bool W_FAST>
 __global__ void __launch_bounds__(PROJ_THREADS)
-cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long long sN, long long sC, long long sH,
-                   long long sW, const float *__restrict__ fl_in, long long fN, long long fC,
-                   const float *__restrict__ cd_in, long long dN, long long dC, int R, float qscale, VoxWorkspace ws,
-                   int fast_shift) {
+cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long long sN, long long sC, int sH, int sW,
+                   const float *__restrict__ fl_in, long long fN, long long fC, const float *__restrict__ cd_in,
+                   long long dN, long long dC, int R, float qscale, VoxWorkspace ws, int fast_shift) {
   extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
   const int map = blockIdx.y;
-  const int n = map / C, c = map - n * C;
+  int n = map, c = 0;
+  if (C != 1) {
+    n = map / C;
+    c = map - n * C;
+  }
   const int P = H * W;
   const float *dmap = depth + n * sN + c * sC;
   const float fl = fl_in[n * fN + c * fC];
@@ -88,16 +92,19 @@ cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long lo
   }
 
   const int p0 = blockIdx.x * (PROJ_THREADS * PROJ_PIX) + threadIdx.x;
+  auto coords = [&](int p, int &h, int &w) {
+    const int slow = fast_shift >= 0 ? (p >> fast_shift) : (p / fast);
+    const int fst = p - slow * fast;
+    h = W_FAST ? slow : fst;
+    w = W_FAST ? fst : slow;
+  };
   float d[PROJ_PIX];
-  int hh[PROJ_PIX], ww[PROJ_PIX];
 #pragma unroll
   for (int k = 0; k < PROJ_PIX; ++k) {
     const int p = p0 + k * PROJ_THREADS;
-    const int slow = fast_shift >= 0 ? (p >> fast_shift) : (p / fast);
-    const int fst = p - slow * fast;
-    hh[k] = W_FAST ? slow : fst;
-    ww[k] = W_FAST ? fst : slow;
-    d[k] = (p < P) ? dmap[hh[k] * sH + ww[k] * sW] : -1.0f;
+    int h, w;
+    coords(p, h, w);
+    d[k] = (p < P) ? __ldg(dmap + (h * sH + w * sW)) : -1.0f;
   }
   unsigned gv[PROJ_PIX], q[PROJ_PIX];
 #pragma unroll
@@ -106,7 +113,9 @@ cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long lo
     q[k] = 0;
     // reference skips only d < 0 (back_projection_kernel.cu:225)
     if (!(d[k] < 0.0f) && (zero_in_bounds || d[k] != 0.0f)) {
-      const CamPoint pt = cam_unproject(d[k], fl, dfl, cam_dist, hh[k], ww[k], Hm1, Wm1, R, grid.Rf);
+      int h, w;
+      coords(p0 + k * PROJ_THREADS, h, w);
+      const CamPoint pt = cam_unproject(d[k], fl, dfl, cam_dist, h, w, Hm1, Wm1, R, grid.Rf);
       if (pt.in_bounds) {
         const float dx = __fadd_rn(pt.gx, -vox_centre(pt.ix, grid));
         const float dy = __fadd_rn(pt.gy, -vox_centre(pt.iy, grid));
@@ -129,6 +138,12 @@ static int cam_check(const float *depth, int64_t N, int64_t C, int64_t H, int64_
   return vox_check_common(N * C, H * W, res);
 }
 
+// offsets inside one map must fit 32 bits (the kernels add them to a 64-bit per-map base)
+static bool map_offsets_fit(int64_t H, int64_t W, int64_t sH, int64_t sW) {
+  const long double span = (long double)(H - 1) * (long double)llabs(sH) + (long double)(W - 1) * (long double)llabs(sW);
+  return span < 2147483647.0L;
+}
+
 static inline int log2_exact(int64_t v) {
   if (v <= 0 || (v & (v - 1))) return -1;
   int s = 0;
@@ -145,12 +160,15 @@ static int cam_project_launch(const float *depth, int64_t N, int64_t C, int64_t 
   const float qscale = (float)res * 16777216.0f;
   const bool w_fast = llabs(sW) <= llabs(sH);  // map consecutive threads to the denser image axis
   const size_t smem = (size_t)w.ntiles * 4;
+  GB_REQUIRE(map_offsets_fit(H, W, sH, sW), GENRE_B200_EINVAL, "cam_bp: depth strides too large");
   if (w_fast)
-    cam_project_kernel<true><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, sH, sW, fl, fN,
-                                                              fC, camdist, dN, dC, res, qscale, w, log2_exact(W));
+    cam_project_kernel<true><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, (int)sH, (int)sW,
+                                                              fl, fN, fC, camdist, dN, dC, res, qscale, w,
+                                                              log2_exact(W));
   else
-    cam_project_kernel<false><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, sH, sW, fl, fN,
-                                                               fC, camdist, dN, dC, res, qscale, w, log2_exact(H));
+    cam_project_kernel<false><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, (int)sH,
+                                                               (int)sW, fl, fN, fC, camdist, dN, dC, res, qscale, w,
+                                                               log2_exact(H));
   return check_launch("cam_bp project kernel");
 }
 
