@@ -1,0 +1,73 @@
+"""Harness that lets the reference's FROZEN caller files (models/*.py, util/*.py ...) import and run on a current
+PyTorch on top of this package, without editing or copying them.
+
+    import genre_shapehd_b200.compat as compat
+    compat.bootstrap("/path/to/GenRe-ShapeHD")     # then: from models.genre_full_model import Net
+
+What it does:
+  * genre_shapehd_b200.install(reference_root): toolbox / nndistance / networks resolve HERE, everything else
+    (models, util, loggers, visualize, datasets, options, networks.uresnet/revresnet) in the reference checkout;
+  * stubs the optional third-party modules the frozen files import at module level but never use on the
+    differentiable path (skimage, trimesh; visualize/visualizer.py:8, util/util_sph.py:1-3);
+  * makes torchvision's resnet18(pretrained=True) build offline (random init) — there is no network here.
+"""
+import os
+import sys
+import types
+
+import genre_shapehd_b200
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    try:
+        return __import__(name)
+    except Exception:
+        pass
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__genre_b200_stub__ = True
+    sys.modules[name] = m
+    return m
+
+
+def _unavailable(what):
+    def f(*a, **k):
+        raise RuntimeError("%s is not available in this environment (stubbed by genre_shapehd_b200.compat)" % what)
+    return f
+
+
+def bootstrap(reference_root=None, offline_resnet=True):
+    root = reference_root or os.environ.get("GENRE_REF") or "/root/reference"
+    if not os.path.isdir(os.path.join(root, "models")):
+        raise FileNotFoundError("no GenRe-ShapeHD checkout at %r" % root)
+    os.environ.setdefault("GENRE_REF", root)
+    genre_shapehd_b200.install(root)
+    sk = _stub("skimage")
+    if getattr(sk, "__genre_b200_stub__", False):
+        measure = _stub("skimage.measure", marching_cubes_lewiner=_unavailable("skimage.measure.marching_cubes"),
+                        marching_cubes=_unavailable("skimage.measure.marching_cubes"))
+        sk.measure = measure
+        _stub("skimage.io", imread=_unavailable("skimage.io.imread"), imsave=_unavailable("skimage.io.imsave"))
+        _stub("skimage.transform", resize=_unavailable("skimage.transform.resize"))
+    tm = _stub("trimesh")
+    if getattr(tm, "__genre_b200_stub__", False):
+        tm.Trimesh = _unavailable("trimesh.Trimesh")
+        tm.load = _unavailable("trimesh.load")
+    if offline_resnet:
+        import torchvision.models as tvm
+        if not getattr(tvm.resnet18, "__genre_b200_offline__", False):
+            orig = tvm.resnet18
+
+            def resnet18(pretrained=False, **kw):  # the frozen files pass pretrained=True (uresnet.py:16,87)
+                kw.pop("weights", None)
+                return orig(weights=None, **kw)
+            resnet18.__genre_b200_offline__ = True
+            tvm.resnet18 = resnet18
+            try:
+                import torchvision.models.resnet as tvr
+                tvr.resnet18 = resnet18
+            except Exception:
+                pass
+    return root
