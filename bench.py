@@ -157,23 +157,19 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
-    import torch.distributed as dist
 
     import genre_shapehd_b200
     genre_shapehd_b200.install()
-    from genre_shapehd_b200 import _lib
+    from genre_shapehd_b200 import _lib, dist_util
     from genre_shapehd_b200.synth import bench_depth_batch
     from toolbox.cam_bp.cam_bp.modules.camera_backprojection_module import Camera_back_projection_layer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = dist_util.env_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dist_util.init("nccl", dev)
     _lib.load()
 
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
@@ -183,16 +179,10 @@ def run_b200(args):
     inputs = [torch.from_numpy(host).to(dev).clone() for _ in range(n_in)]
 
     def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
+        dist_util.barrier(dev)
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return dist_util.max_over_ranks(ms, dev)
 
     # ---- leg 1: inputs resident in HBM --------------------------------------------------------------
     use_graph = not args.no_graph
@@ -340,8 +330,7 @@ def run_b200(args):
                 "gpu_launches": launches, "launch_mode": "cuda_graph" if use_graph else "python",
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    dist_util.finalize()
 
 
 def main():
