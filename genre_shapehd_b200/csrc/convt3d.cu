@@ -1,0 +1,383 @@
+// convt3d.cu — stride-2 ConvTranspose3d forward as a tcgen05 (5th-gen tensor core) implicit GEMM, TF32 in / FP32 out.
+//
+// Reference layers: networks/networks.py:162-167 (Unet_3D.dec2..dec6 = Deconv3d_skip: cat(x, skip) ->
+// ConvTranspose3d(k, s=2, p) [-> BatchNorm3d -> LeakyReLU]), :253-256,:40-57 (VoxelDecoder / VoxelGenerator
+// deconv3d_2x).  The dominant one, dec5 = ConvT(80 -> 20, k=8, s=2, p=3) on 32^3, is 53.7 of Unet_3D's 78 GFLOP.
+//
+// Formulation.  o = 2 i - p + k splits the output into 8 parity classes (o = 2 j + par); class `par` only sees
+// the taps k = k0 + 2 t, t < T = K/2, at input positions i = j + base - t: a stride-1 T^3-tap convolution.
+//     GEMM per class:  M = B * D*H*W positions,  N = Cout (padded to NPAD),  K = T^3 * Cin
+// Activations are kept channel-BLOCKED: [B*D][C/4][H][W][4] (16 bytes per position and channel group), so
+//   * a shared-memory halo [cg][y][x][4] is exactly tcgen05's canonical K-major NO-SWIZZLE operand layout
+//     (core matrix = 8 consecutive x positions x 16 B; next y row = SBO; next channel group = LBO), and
+//   * the operand of ANY tap is the same halo at a different 16-byte-aligned start address: one halo load feeds
+//     T*T (y,x) taps and MT M-tiles, which is what keeps the kernel off the L2 bandwidth wall at N = 20.
+// The two sources of the skip concatenation are two tensors walked one after the other along K (the cat is never
+// materialised).  Weights are pre-packed on the host into the exact shared-memory image of each (parity, z-tap,
+// K-chunk) stage and arrive with ONE cp.async.bulk per stage.
+//
+// CTA = one (b, z, 16 y-rows, full W) output slab of one parity class: MT = W/8 M-tiles of 128 rows, accumulators
+// MT x NPAD fp32 columns in TMEM.  Warps 0-3: halo producers (cp.async 16 B, zero-fill = padding), then epilogue
+// (tcgen05.ld -> scale/shift/LeakyReLU -> blocked store).  Warp 4: TMEM allocation + single-thread MMA issue.
+// Pipeline: STAGES-deep ring of (halo chunk, weight chunk) with full/empty mbarriers; tcgen05.commit frees a slot.
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int CT_THREADS = 160;       // 4 producer/epilogue warps + 1 MMA warp
+constexpr int CT_PRODUCERS = 128;
+constexpr int CT_BY = 16;             // y rows per CTA (16 core-matrix groups of 8 x positions = M 128)
+constexpr int CT_KCG = 2;             // channel groups (of 4) per stage = one K=8 TF32 MMA per tap and M-tile
+
+struct ConvTParams {
+  const float *src0, *src1;  // blocked activations [B*D][cg][H][W][4]; src1 may be null (cg1 = 0)
+  int cg0, cg1;
+  int B, D, H, W;            // input extent
+  const float *wpack;        // [8 parity][T ztap][nchunk][T*T taps][2 kcore][NPAD/8][8][4]
+  const float *scale, *shift;  // per output channel (NPAD entries): y = act(acc * scale + shift)
+  float slope;               // LeakyReLU slope (1 = identity)
+  float *out;                // blocked [B*2D][cgo][2H][2W][4]
+  int cgo;                   // output channel groups
+  int base[2];               // input index = j + base[par] - t
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 26)) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void cp_async16_zfill(void *sdst, const void *gsrc, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// start >> 4 | LBO >> 4 (K-direction core-matrix stride) << 16 | SBO >> 4 (M/N-direction 8-row group stride) << 32
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::tf32 instruction descriptor: D fp32, A/B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------
+// T: taps per dimension of a parity class (K/2: 2 for k=4, 4 for k=8); NPAD: padded Cout (32 or 64); MT = W/8.
+template <int T, int NPAD, int MT>
+struct ConvTCfg {
+  static constexpr int W = 8 * MT;
+  static constexpr int PY = CT_BY + T - 1, PX = W + T - 1;     // halo extent
+  static constexpr int A_CG_BYTES = PY * PX * 16;              // one channel group of the halo = LBO of A
+  static constexpr int A_BYTES = CT_KCG * A_CG_BYTES;
+  static constexpr int B_TAP_BYTES = 2 * (NPAD / 8) * 128;     // one (y,x) tap: [2 kcore][NPAD/8][8 rows][16 B]
+  static constexpr int B_BYTES = T * T * B_TAP_BYTES;
+  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 127) / 128) * 128;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = MT * NPAD <= 32 ? 32 : MT * NPAD <= 64 ? 64 : MT * NPAD <= 128 ? 128 : MT * NPAD <= 256 ? 256 : 512;
+  static constexpr int POS = PY * PX;
+  static constexpr int POS_PER_THREAD = (POS + CT_PRODUCERS - 1) / CT_PRODUCERS;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
+  static_assert(STAGES >= 2, "stage too large");
+  static_assert(MT * NPAD <= 512, "accumulators exceed TMEM");
+};
+
+template <int T, int NPAD, int MT>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+convt3d_s2_kernel(const ConvTParams p) {
+  using Cfg = ConvTCfg<T, NPAD, MT>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t *stages = smem;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t *empty = full + Cfg::STAGES;
+  uint64_t *accum_full = empty + Cfg::STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int par = blockIdx.y;  // parity class: bit 2 = z, bit 1 = y, bit 0 = x
+  const int pz = (par >> 2) & 1, py = (par >> 1) & 1, px = par & 1;
+  const int ytiles = p.H / CT_BY;
+  const int yt = blockIdx.x % ytiles;
+  const int zj = (blockIdx.x / ytiles) % p.D;
+  const int b = blockIdx.x / (ytiles * p.D);
+  const int y0 = yt * CT_BY;
+  const int nchunk = (p.cg0 + p.cg1) / CT_KCG;
+
+  // valid z taps of this slab (a tap plane outside the input contributes nothing: skipped by both sides)
+  int ztaps[T], nz = 0;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int zi = zj + p.base[pz] - t;
+    if (zi >= 0 && zi < p.D) ztaps[nz++] = t;
+  }
+  const int n_stages_total = nz * nchunk;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], CT_PRODUCERS + 1);  // 128 producer arrivals + the expect_tx arrival of the weight copy
+      mbar_init(&empty[s], 1);                // one tcgen05.commit
+    }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {  // TMEM allocation is warp-wide
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers: halo (cp.async, zero-fill) + weights (one bulk copy per stage) ==========
+    // this thread's halo positions are the same for every stage: precompute (offset in cg plane, y, x, validity)
+    int hoff[Cfg::POS_PER_THREAD], gy[Cfg::POS_PER_THREAD], gx[Cfg::POS_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
+      const int idx = tid + i * CT_PRODUCERS;
+      const int hy = idx / Cfg::PX, hx = idx - hy * Cfg::PX;
+      hoff[i] = idx < Cfg::POS ? idx * 16 : -1;
+      gy[i] = y0 + p.base[py] - (T - 1) + hy;  // halo row hy holds input row y0 + base - (T-1) + hy
+      gx[i] = p.base[px] - (T - 1) + hx;
+    }
+    constexpr int LAG = Cfg::STAGES - 1 < 2 ? 1 : 2;  // cp.async groups in flight before a stage is published
+    for (int it = 0; it < n_stages_total + LAG; ++it) {
+      if (it < n_stages_total) {
+        const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
+        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+        const int zt = ztaps[it / nchunk], kc = it % nchunk;
+        uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
+        if (tid == 0) {
+          const float *wsrc = p.wpack + ((((size_t)par * T + zt) * nchunk + kc) * (size_t)(Cfg::B_BYTES / 4));
+          mbar_arrive_expect_tx(&full[s], Cfg::B_BYTES);
+          bulk_g2s(sa + Cfg::A_BYTES, wsrc, Cfg::B_BYTES, &full[s]);
+        }
+        const int zi = zj + p.base[pz] - zt;
+#pragma unroll
+        for (int c = 0; c < CT_KCG; ++c) {
+          int cg = kc * CT_KCG + c;
+          const float *src = p.src0;
+          int ncg = p.cg0;
+          if (cg >= p.cg0) { cg -= p.cg0; src = p.src1; ncg = p.cg1; }
+          const float *plane = src + ((((size_t)b * p.D + zi) * ncg + cg) * p.H) * (size_t)p.W * 4;
+#pragma unroll
+          for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
+            if (hoff[i] < 0) continue;
+            const bool ok = (gy[i] >= 0) & (gy[i] < p.H) & (gx[i] >= 0) & (gx[i] < p.W);
+            const float *g = ok ? plane + ((size_t)gy[i] * p.W + gx[i]) * 4 : plane;
+            cp_async16_zfill(sa + c * Cfg::A_CG_BYTES + hoff[i], g, ok);
+          }
+        }
+      }
+      cp_async_commit();
+      if (it >= LAG) {  // the group of stage (it - LAG) has landed: publish it to the tensor-core (async) proxy
+        cp_async_wait<LAG>();
+        fence_proxy_async_smem();
+        mbar_arrive(&full[(it - LAG) % Cfg::STAGES]);
+      }
+    }
+
+    // ===================== epilogue: TMEM -> registers -> act(acc*scale+shift) -> blocked global store =========
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int m = warp * 32 + lane;  // accumulator row = TMEM lane
+    const int yy = m >> 3, xx = m & 7;
+    const int Ho = 2 * p.H, Wo = 2 * p.W, Do = 2 * p.D;
+    const int oz = 2 * zj + pz, oy = 2 * (y0 + yy) + py;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int ox = 2 * (8 * mt + xx) + px;
+#pragma unroll
+      for (int nb = 0; nb < NPAD / 32; ++nb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + nb * 32), v);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const int cgo = nb * 8 + g4;
+          if (cgo < p.cgo) {
+            float4 o;
+            float *po = &o.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = cgo * 4 + e;
+              float t = fmaf(v[g4 * 4 + e], __ldg(p.scale + n), __ldg(p.shift + n));
+              po[e] = t > 0.0f ? t : t * p.slope;
+            }
+            float *dst = p.out + (((((size_t)b * Do + oz) * p.cgo + cgo) * Ho + oy) * (size_t)Wo + ox) * 4;
+            *reinterpret_cast<float4 *>(dst) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (lane == 0) {
+    // ===================== MMA issuer (one thread) =============================================================
+    constexpr uint32_t idesc = umma_idesc_tf32(128, NPAD);
+    bool first = true;
+    for (int it = 0; it < n_stages_total; ++it) {
+      const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
+      mbar_wait(&full[s], use & 1);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
+      const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+      for (int ty = 0; ty < T; ++ty) {
+#pragma unroll
+        for (int tx = 0; tx < T; ++tx) {
+          const uint64_t bdesc = umma_desc(sb + (ty * T + tx) * Cfg::B_TAP_BYTES, (NPAD / 8) * 128, 128);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            // rows of this M-tile under tap (ty,tx): halo row (T-1-ty) + y, column (T-1-tx) + 8*mt + x
+            const uint32_t a0 = sa + (((T - 1 - ty) * Cfg::PX) + (T - 1 - tx) + 8 * mt) * 16;
+            umma_tf32(tmem_base + mt * NPAD, umma_desc(a0, Cfg::A_CG_BYTES, Cfg::PX * 16), bdesc, idesc, !first || (ty | tx));
+          }
+        }
+      }
+      first = false;
+      umma_commit(&empty[s]);  // frees the slot when the MMAs that read it are done (implies fence::before_thread_sync)
+    }
+    if (n_stages_total == 0) {
+      // cannot happen for a valid layer (every output has at least one z tap); keep the protocol sound anyway
+    }
+    umma_commit(accum_full);
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+template <int T, int NPAD, int MT>
+static int launch_convt(const ConvTParams &p, cudaStream_t st) {
+  using Cfg = ConvTCfg<T, NPAD, MT>;
+  auto kern = convt3d_s2_kernel<T, NPAD, MT>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("convt3d: cudaFuncSetAttribute(%zu bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured[dev & 63] = true;
+  }
+  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY)), 8);
+  kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(p);
+  return check_launch("convt3d_s2 kernel");
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+// ConvTranspose3d(kernel K in {4, 8}, stride 2, padding K/2 - 1) forward on channel-blocked activations.
+//   src0 [B*D][cg0][H][W][4], src1 [B*D][cg1][H][W][4] or NULL: the two halves of the channel concatenation
+//   wpack: weights packed by genre_shapehd_b200.ops_conv.pack_convt_weights (layout in the kernel header)
+//   scale, shift [npad]: per-channel affine applied to the accumulator (bias and folded eval-mode BatchNorm),
+//   slope: LeakyReLU slope (1 = none).   out [B*2D][cgo][2H][2W][4]
+// Supported: W in {16, 32}, H % 16 == 0, (cg0 + cg1) even, cg0 even, 4*cgo <= npad, npad in {32, 64}.
+extern "C" int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const float *src1, int cg1, int64_t B,
+                                             int64_t D, int64_t H, int64_t W, const float *wpack, int ksize, int npad,
+                                             const float *scale, const float *shift, float slope, float *out, int cgo,
+                                             void *stream) {
+  GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "convt3d: null pointer");
+  GB_REQUIRE(ksize == 4 || ksize == 8, GENRE_B200_EINVAL, "convt3d: kernel size %d unsupported (4 or 8)", ksize);
+  GB_REQUIRE(npad == 32 || npad == 64, GENRE_B200_EINVAL, "convt3d: npad %d unsupported (32 or 64)", npad);
+  GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "convt3d: input width %lld unsupported (16 or 32)", (long long)W);
+  GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt3d: bad extent");
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && cg0 % CT_KCG == 0 && cg1 % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "convt3d: channel groups (%d, %d) must be even", cg0, cg1);
+  GB_REQUIRE(cgo > 0 && 4 * cgo <= npad, GENRE_B200_EINVAL, "convt3d: %d output channels exceed npad %d", 4 * cgo, npad);
+  GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "convt3d: grid too large");
+  GB_REQUIRE(aligned16(src0) && aligned16(wpack) && aligned16(out) && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,
+             "convt3d: buffers must be 16-byte aligned");
+  ConvTParams p;
+  p.src0 = src0; p.src1 = src1; p.cg0 = cg0; p.cg1 = cg1;
+  p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
+  p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  const int pad = ksize / 2 - 1;
+  for (int par = 0; par < 2; ++par) {
+    const int k0 = (par + pad) % 2;
+    p.base[par] = (par + pad - k0) / 2;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int T = ksize / 2;
+#define GB_CT(TT, NN, MM) return launch_convt<TT, NN, MM>(p, st)
+  if (T == 4 && npad == 32 && W == 32) GB_CT(4, 32, 4);
+  if (T == 4 && npad == 32 && W == 16) GB_CT(4, 32, 2);
+  if (T == 2 && npad == 32 && W == 32) GB_CT(2, 32, 4);
+  if (T == 2 && npad == 32 && W == 16) GB_CT(2, 32, 2);
+  if (T == 2 && npad == 64 && W == 32) GB_CT(2, 64, 4);
+  if (T == 2 && npad == 64 && W == 16) GB_CT(2, 64, 2);
+  if (T == 4 && npad == 64 && W == 32) GB_CT(4, 64, 4);
+  if (T == 4 && npad == 64 && W == 16) GB_CT(4, 64, 2);
+#undef GB_CT
+  return fail_arg(GENRE_B200_EINVAL, "convt3d: no kernel instance for k=%d npad=%d W=%lld", ksize, npad, (long long)W);
+}

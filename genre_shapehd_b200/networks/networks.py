@@ -198,7 +198,11 @@ class Deconv3d_skip(nn.Module):
         self.net = nn.Sequential(deconv, nn.BatchNorm3d(ncout), nn.LeakyReLU()) if is_activate else deconv
 
     def forward(self, x, skip_in):
-        return self.net(cat((x, skip_in), dim=1))
+        if isinstance(self.net, nn.Sequential):
+            y = ops_conv.deconv_skip(x, skip_in, self.net[0], self.net[1], self.net[2].negative_slope)
+        else:
+            y = ops_conv.deconv_skip(x, skip_in, self.net)
+        return y if y is not None else self.net(cat((x, skip_in), dim=1))
 
 
 class Unet_3D(nn.Module):

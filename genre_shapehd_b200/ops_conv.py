@@ -1,14 +1,100 @@
 """Dispatch of the 3D convolutions of networks/networks.py to the hand-written sm_100a kernels.
 
-``conv3d(x, module)`` / ``conv_transpose3d(x, module)`` return the result computed by this library's kernels, or
-``None`` when no kernel covers the layer (shape / dtype / device / autograd mode) — the caller then runs the layer
-the way the reference does (torch.nn -> cuDNN).  Which layers are covered is stated in DESIGN.md.
+``conv3d(x, module)`` / ``conv_transpose3d(x, module)`` / ``deconv_skip(...)`` return the result computed by this
+library's tcgen05 kernels, or ``None`` when no kernel covers the layer (shape / dtype / device / autograd) — the
+caller then runs the layer the way the reference does (torch.nn -> cuDNN).
+
+Covered in this round (csrc/convt3d.cu): ConvTranspose3d(k in {4, 8}, stride 2, padding k/2-1) FORWARD, without
+autograd, input width 16 or 32, height a multiple of 16, Cin a multiple of 8, Cout <= 64: Unet_3D.dec4 / dec5,
+VoxelDecoder / VoxelGenerator stages at 16^3 and 32^3.  TF32 operands, FP32 accumulation (the cuDNN path the
+reference runs on current PyTorch uses TF32 by default as well).
+
+Activations cross the kernel in a channel-blocked layout [B*D][C/4][H][W][4]; ``to_blocked`` / ``from_blocked``
+convert at the boundary.
 """
 import os
 
 import torch
 
+from . import _lib
+
 ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
+_wcache = {}
+
+
+def to_blocked(x):
+    """NCDHW [B,C,D,H,W] (C % 4 == 0) -> [B*D, C/4, H, W, 4] contiguous."""
+    b, c, d, h, w = x.shape
+    return x.reshape(b, c // 4, 4, d, h, w).permute(0, 3, 1, 4, 5, 2).contiguous().view(b * d, c // 4, h, w, 4)
+
+
+def from_blocked(y, batch, channels):
+    """[B*D, cg, H, W, 4] -> NCDHW [B, channels, D, H, W] (drops channel padding)."""
+    bd, cg, h, w, _ = y.shape
+    d = bd // batch
+    return y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
+
+
+def pack_convt_weights(weight, npad):
+    """ConvTranspose3d weight [Cin, Cout, K, K, K] -> the per-stage shared-memory images the kernel bulk-copies:
+    [8 parity][T z-tap][Cin/8 chunk][T*T (y,x) taps][2 k-core][npad/8 n-group][8 n][4 k]  (T = K/2)."""
+    cin, cout, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    t, pad = k // 2, k // 2 - 1
+    k0 = [(p + pad) % 2 for p in (0, 1)]
+    wp = weight.new_zeros((cin, npad, k, k, k))
+    wp[:, :cout] = weight
+    out = weight.new_empty((2, 2, 2, t, cin // 8, t, t, 2, npad // 8, 8, 4))
+    for pz in (0, 1):
+        for py in (0, 1):
+            for px in (0, 1):
+                sub = wp[:, :, k0[pz]::2, k0[py]::2, k0[px]::2]                      # [Cin, npad, tz, ty, tx]
+                sub = sub.reshape(cin // 8, 2, 4, npad // 8, 8, t, t, t)              # (kc, kk, e, ng, r, tz, ty, tx)
+                out[pz, py, px] = sub.permute(5, 0, 6, 7, 1, 3, 4, 2)                 # (tz, kc, ty, tx, kk, ng, r, e)
+    return out.contiguous()
+
+
+def _packed(module, npad):
+    w = module.weight
+    key = (id(module), npad)
+    ver = (w._version, w.data_ptr(), w.device)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, pack_convt_weights(w.detach(), npad))
+        _wcache[key] = hit
+    return hit[1]
+
+
+def _convt_supported(shape_bcdhw, module):
+    b, c, d, h, w = shape_bcdhw
+    k = module.kernel_size[0]
+    return (ENABLED and tuple(module.kernel_size) == (k, k, k) and k in (4, 8) and tuple(module.stride) == (2, 2, 2)
+            and tuple(module.padding) == (k // 2 - 1,) * 3 and tuple(module.output_padding) == (0, 0, 0)
+            and tuple(module.dilation) == (1, 1, 1) and module.groups == 1 and w in (16, 32) and h % 16 == 0
+            and c % 8 == 0 and module.out_channels <= 64)
+
+
+def convt3d_s2_blocked(src0, src1, batch, module, scale=None, shift=None, slope=1.0):
+    """Run the kernel on blocked inputs; returns the blocked output [B*2D, cgo, 2H, 2W, 4]."""
+    bd, cg0, h, w, _ = src0.shape
+    cg1 = src1.shape[1] if src1 is not None else 0
+    cout = module.out_channels
+    npad = 32 if cout <= 32 else 64
+    cgo = (cout + 3) // 4
+    wpack = _packed(module, npad)
+    dev = src0.device
+    sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
+    if shift is None:
+        shift = module.bias.detach() if module.bias is not None else torch.zeros(cout, device=dev)
+    sh = torch.nn.functional.pad(shift.float(), (0, npad - cout))
+    out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=dev, dtype=torch.float32)
+    _lib.call("genre_b200_convt3d_s2_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None, cg1,
+              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, sc.data_ptr(), sh.data_ptr(),
+              float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
+    return out
+
+
+def _no_autograd(*tensors):
+    return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
 
 def conv3d(x, m):
@@ -16,4 +102,29 @@ def conv3d(x, m):
 
 
 def conv_transpose3d(x, m):
-    return None
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_supported(x.shape, m)
+            and _no_autograd(x, m.weight, m.bias)):
+        return None
+    y = convt3d_s2_blocked(to_blocked(x), None, x.shape[0], m)
+    return from_blocked(y, x.shape[0], m.out_channels)
+
+
+def deconv_skip(x, skip, conv, bn=None, slope=None):
+    """cat(x, skip) -> ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> LeakyReLU(slope)] with the
+    concatenation walked as two K ranges instead of being materialised.  None if not covered."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
+            and x.shape[1] % 8 == 0 and skip.shape[1] % 8 == 0
+            and _convt_supported((x.shape[0], x.shape[1] + skip.shape[1]) + tuple(x.shape[2:]), conv)
+            and _no_autograd(x, skip, conv.weight, conv.bias)):
+        return None
+    scale = shift = None
+    if bn is not None:
+        if bn.training or not bn.track_running_stats:
+            return None  # batch statistics need the un-normalised output first
+        inv = torch.rsqrt(bn.running_var + bn.eps)
+        scale = inv * (bn.weight if bn.weight is not None else 1.0)
+        bias = conv.bias.detach() if conv.bias is not None else torch.zeros_like(bn.running_mean)
+        shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
+    y = convt3d_s2_blocked(to_blocked(x), to_blocked(skip), x.shape[0], conv, scale, shift,
+                           1.0 if slope is None else slope)
+    return from_blocked(y, x.shape[0], conv.out_channels)

@@ -168,6 +168,23 @@ int genre_b200_voxelize_stage_splat(int64_t n_maps, int64_t pixels_per_map, int 
                                     float *tdf, float *cnt, float hit_alpha, float hit_beta, float background,
                                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * ConvTranspose3d(kernel K in {4, 8}, stride 2, padding K/2 - 1) forward as a tcgen05 implicit GEMM (TF32 operands,
+ * FP32 accumulation in TMEM).  Replaces the cuDNN call behind nn.ConvTranspose3d in networks/networks.py:211-222
+ * (Unet_3D Deconv3d_skip: the channel concatenation of :221 is walked as two K ranges, never materialised) and
+ * :253-256 (deconv3d_2x of VoxelDecoder / VoxelGenerator).
+ *   src0 [B*D][cg0][H][W][4], src1 [B*D][cg1][H][W][4] or NULL   channel-blocked activations (cg = channels/4)
+ *   wpack   weights packed per (parity, z-tap, 8-channel chunk) stage: see genre_shapehd_b200/ops_conv.py
+ *   scale, shift [npad]   y = act(acc * scale + shift): bias and folded eval-mode BatchNorm3d
+ *   slope   LeakyReLU slope (1 = none);   out [B*2D][cgo][2H][2W][4]
+ * Supported: W in {16,32}, H % 16 == 0, cg0, cg1 even, 4*cgo <= npad, npad in {32,64}.
+ * ------------------------------------------------------------------------------------------- */
+int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const float *src1, int cg1,
+                                  int64_t B, int64_t D, int64_t H, int64_t W,
+                                  const float *wpack, int ksize, int npad,
+                                  const float *scale, const float *shift, float slope,
+                                  float *out, int cgo, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,62 @@
+"""tcgen05 ConvTranspose3d kernel (csrc/convt3d.cu) against torch's fp32 conv_transpose3d (TF32 off)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from genre_shapehd_b200 import ops_conv
+import networks.networks as nets
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref(x, m):
+    torch.backends.cudnn.allow_tf32 = False
+    return F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding)
+
+
+@pytest.mark.parametrize("k,cin,cout,b,d,h,w", [(4, 8, 4, 1, 1, 16, 16), (8, 8, 20, 1, 2, 16, 16), (8, 80, 20, 2, 4, 32, 32),
+                                                 (4, 64, 32, 1, 3, 32, 32), (4, 128, 64, 2, 2, 16, 16), (8, 16, 40, 1, 2, 32, 16)])
+def test_convt3d_vs_torch(k, cin, cout, b, d, h, w):
+    torch.manual_seed(k * 1000 + cin + cout)
+    m = nets.ConvTranspose3d(cin, cout, k, 2, k // 2 - 1).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV)
+    with torch.no_grad():
+        y = ops_conv.conv_transpose3d(x, m)
+        assert y is not None, "layer should be covered by the custom kernel"
+        ref = _ref(x, m)
+    assert y.shape == ref.shape
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 4e-3 * scale, "max err %g vs scale %g" % (err, scale)   # TF32 operands (10-bit mantissa)
+
+
+def test_blocked_layout_roundtrip():
+    x = torch.randn(2, 24, 3, 16, 16, device=DEV)
+    assert torch.equal(ops_conv.from_blocked(ops_conv.to_blocked(x), 2, 24), x)
+
+
+def test_deconv_skip_fused_bn_leaky_vs_torch():
+    torch.manual_seed(5)
+    blk = nets.Deconv3d_skip(80, 20, 8, 2, 3, 0).to(DEV).eval()
+    blk.net[1].running_mean.normal_(0, 0.1)
+    blk.net[1].running_var.uniform_(0.5, 1.5)
+    blk.net[1].weight.data.uniform_(0.5, 1.5)
+    blk.net[1].bias.data.normal_(0, 0.1)
+    x, s = torch.randn(1, 40, 2, 32, 32, device=DEV), torch.randn(1, 40, 2, 32, 32, device=DEV)
+    with torch.no_grad():
+        y = blk(x, s)
+        torch.backends.cudnn.allow_tf32 = False
+        ref = blk.net(torch.cat((x, s), 1))
+    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+def test_autograd_and_unsupported_shapes_fall_back():
+    m = nets.ConvTranspose3d(8, 4, 4, 2, 1).to(DEV)
+    x = torch.randn(1, 8, 2, 16, 16, device=DEV, requires_grad=True)
+    assert ops_conv.conv_transpose3d(x, m) is None             # autograd: cuDNN path
+    y = m(x)
+    y.sum().backward()
+    assert x.grad is not None
+    with torch.no_grad():
+        assert ops_conv.conv_transpose3d(torch.randn(1, 8, 2, 8, 8, device=DEV), m) is None   # W=8 not covered
