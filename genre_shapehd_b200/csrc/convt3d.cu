@@ -135,7 +135,7 @@ struct ConvTCfg {
   static constexpr int B_TAP_BYTES = 2 * (NPAD / 8) * 128;     // one (y,x) tap: [2 kcore][NPAD/8][8 rows][16 B]
   static constexpr int B_BYTES = T * T * B_TAP_BYTES;
   static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 127) / 128) * 128;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (218 * 1024) / STAGE_BYTES > 6 ? 6 : (218 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = MT * NPAD <= 32 ? 32 : MT * NPAD <= 64 ? 64 : MT * NPAD <= 128 ? 128 : MT * NPAD <= 256 ? 256 : 512;
   static constexpr int POS = PY * PX;
   static constexpr int POS_PER_THREAD = (POS + CT_PRODUCERS - 1) / CT_PRODUCERS;
@@ -144,7 +144,9 @@ struct ConvTCfg {
   static_assert(MT * NPAD <= 512, "accumulators exceed TMEM");
 };
 
-template <int T, int NPAD, int MT>
+// PAR = true : 8 parity classes (blockIdx.y), output at 2*j + parity (ConvTranspose3d stride 2)
+// PAR = false: one class, output at j (stride-1 tap convolution; strided Conv3d arrives here after space-to-depth)
+template <int T, int NPAD, int MT, bool PAR>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 convt3d_s2_kernel(const ConvTParams p) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
@@ -247,11 +249,11 @@ convt3d_s2_kernel(const ConvTParams p) {
     tc_fence_after();
     const int m = warp * 32 + lane;  // accumulator row = TMEM lane
     const int yy = m >> 3, xx = m & 7;
-    const int Ho = 2 * p.H, Wo = 2 * p.W, Do = 2 * p.D;
-    const int oz = 2 * zj + pz, oy = 2 * (y0 + yy) + py;
+    const int Ho = PAR ? 2 * p.H : p.H, Wo = PAR ? 2 * p.W : p.W, Do = PAR ? 2 * p.D : p.D;
+    const int oz = PAR ? 2 * zj + pz : zj, oy = PAR ? 2 * (y0 + yy) + py : y0 + yy;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const int ox = 2 * (8 * mt + xx) + px;
+      const int ox = PAR ? 2 * (8 * mt + xx) + px : 8 * mt + xx;
 #pragma unroll
       for (int nb = 0; nb < NPAD / 32; ++nb) {
         float v[32];
@@ -313,10 +315,10 @@ convt3d_s2_kernel(const ConvTParams p) {
   }
 }
 
-template <int T, int NPAD, int MT>
+template <int T, int NPAD, int MT, bool PAR>
 static int launch_convt(const ConvTParams &p, cudaStream_t st) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
-  auto kern = convt3d_s2_kernel<T, NPAD, MT>;
+  auto kern = convt3d_s2_kernel<T, NPAD, MT, PAR>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -328,7 +330,7 @@ static int launch_convt(const ConvTParams &p, cudaStream_t st) {
     }
     configured[dev & 63] = true;
   }
-  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY)), 8);
+  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY)), PAR ? 8 : 1);
   kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(p);
   return check_launch("convt3d_s2 kernel");
 }
@@ -369,7 +371,7 @@ extern "C" int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const f
   }
   cudaStream_t st = as_stream(stream);
   const int T = ksize / 2;
-#define GB_CT(TT, NN, MM) return launch_convt<TT, NN, MM>(p, st)
+#define GB_CT(TT, NN, MM) return launch_convt<TT, NN, MM, true>(p, st)
   if (T == 4 && npad == 32 && W == 32) GB_CT(4, 32, 4);
   if (T == 4 && npad == 32 && W == 16) GB_CT(4, 32, 2);
   if (T == 2 && npad == 32 && W == 32) GB_CT(2, 32, 4);
@@ -380,4 +382,42 @@ extern "C" int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const f
   if (T == 4 && npad == 64 && W == 16) GB_CT(4, 64, 2);
 #undef GB_CT
   return fail_arg(GENRE_B200_EINVAL, "convt3d: no kernel instance for k=%d npad=%d W=%lld", ksize, npad, (long long)W);
+}
+
+// Stride-1 convolution with T taps per dimension on channel-blocked activations (same kernel, one output class):
+//     out[b, z, y, x, n] = act(scale[n] * sum_{tz,ty,tx,c} in[b, z + base - tz, y + base - ty, x + base - tx, c] * Wt[...] + shift[n])
+// A strided Conv3d reaches this form through space-to-depth (genre_shapehd_b200/ops_conv.py): Unet_3D.enc1 =
+// Conv3d(2 -> 20, k=8, s=2, p=3) (networks/networks.py:151) is a 5-tap stride-1 convolution over the 16 s2d channels.
+//   wpack [T z-tap][C/8 chunk][T*T taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4]
+// Supported: T in {3, 5}, W in {16, 32, 64}, H % 16 == 0, npad = 32.
+extern "C" int genre_b200_conv3d_taps_forward(const float *src0, int cg0, const float *src1, int cg1, int64_t B,
+                                              int64_t D, int64_t H, int64_t W, const float *wpack, int taps, int base,
+                                              int npad, const float *scale, const float *shift, float slope,
+                                              float *out, int cgo, void *stream) {
+  GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_taps: null pointer");
+  GB_REQUIRE(taps == 3 || taps == 5, GENRE_B200_EINVAL, "conv3d_taps: %d taps unsupported (3 or 5)", taps);
+  GB_REQUIRE(npad == 32, GENRE_B200_EINVAL, "conv3d_taps: npad %d unsupported (32)", npad);
+  GB_REQUIRE(W == 16 || W == 32 || W == 64, GENRE_B200_EINVAL, "conv3d_taps: width %lld unsupported", (long long)W);
+  GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_taps: bad extent");
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && cg0 % CT_KCG == 0 && cg1 % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "conv3d_taps: channel groups (%d, %d) must be even", cg0, cg1);
+  GB_REQUIRE(cgo > 0 && 4 * cgo <= npad, GENRE_B200_EINVAL, "conv3d_taps: too many output channels");
+  GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "conv3d_taps: grid too large");
+  GB_REQUIRE(aligned16(src0) && aligned16(wpack) && aligned16(out) && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,
+             "conv3d_taps: buffers must be 16-byte aligned");
+  ConvTParams p;
+  p.src0 = src0; p.src1 = src1; p.cg0 = cg0; p.cg1 = cg1;
+  p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
+  p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  p.base[0] = p.base[1] = base;
+  cudaStream_t st = as_stream(stream);
+#define GB_CV(TT, MM) return launch_convt<TT, 32, MM, false>(p, st)
+  if (taps == 5 && W == 64) GB_CV(5, 8);
+  if (taps == 5 && W == 32) GB_CV(5, 4);
+  if (taps == 5 && W == 16) GB_CV(5, 2);
+  if (taps == 3 && W == 64) GB_CV(3, 8);
+  if (taps == 3 && W == 32) GB_CV(3, 4);
+  if (taps == 3 && W == 16) GB_CV(3, 2);
+#undef GB_CV
+  return fail_arg(GENRE_B200_EINVAL, "conv3d_taps: no kernel instance");
 }

@@ -26,7 +26,7 @@ class Conv3d(nn.Conv3d):
     """nn.Conv3d parameters + dispatch of the CUDA forward to the sm_100a kernel when one covers the layer."""
 
     def forward(self, x):
-        y = ops_conv.conv3d(x, self)
+        y = ops_conv.conv3d(x, self) if x.is_cuda else None
         return y if y is not None else super().forward(x)
 
 
@@ -186,7 +186,8 @@ class Conv3d_block(nn.Module):
         self.net = nn.Sequential(Conv3d(ncin, ncout, kernel_size, stride, pad), nn.BatchNorm3d(ncout), nn.LeakyReLU())
 
     def forward(self, x):
-        return self.net(x)
+        y = ops_conv.conv3d(x, self.net[0], self.net[1], self.net[2].negative_slope) if x.is_cuda else None
+        return y if y is not None else self.net(x)
 
 
 class Deconv3d_skip(nn.Module):
@@ -198,7 +199,9 @@ class Deconv3d_skip(nn.Module):
         self.net = nn.Sequential(deconv, nn.BatchNorm3d(ncout), nn.LeakyReLU()) if is_activate else deconv
 
     def forward(self, x, skip_in):
-        if isinstance(self.net, nn.Sequential):
+        if not x.is_cuda:
+            y = None
+        elif isinstance(self.net, nn.Sequential):
             y = ops_conv.deconv_skip(x, skip_in, self.net[0], self.net[1], self.net[2].negative_slope)
         else:
             y = ops_conv.deconv_skip(x, skip_in, self.net)

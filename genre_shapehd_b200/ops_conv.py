@@ -94,11 +94,95 @@ def convt3d_s2_blocked(src0, src1, batch, module, scale=None, shift=None, slope=
 
 
 def _no_autograd(*tensors):
+    """The kernels are forward-only and compute in TF32: they run when no gradient is needed and TF32 convolutions
+    are allowed (torch.backends.cudnn.allow_tf32, PyTorch's own switch and default for the cuDNN path they replace)."""
+    if not torch.backends.cudnn.allow_tf32:
+        return False
     return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
 
-def conv3d(x, m):
-    return None
+def space_to_depth_blocked(x):
+    """NCDHW [B,C,D,H,W] (even extents, C*8 % 4 == 0) -> blocked [B*D/2, C*8/4, H/2, W/2, 4] whose channel index is
+    ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px)."""
+    b, c, d, h, w = x.shape
+    t = x.reshape(b, c, d // 2, 2, h // 2, 2, w // 2, 2).permute(0, 2, 1, 3, 5, 7, 4, 6)   # b z' c pz py px y' x'
+    t = t.reshape(b * (d // 2), (c * 8) // 4, 4, h // 2, w // 2).permute(0, 1, 3, 4, 2)
+    return t.contiguous()
+
+
+def pack_conv_k8s2_weights(weight, npad):
+    """Conv3d weight [Cout, Cin, 8, 8, 8] (stride 2, padding 3) -> the equivalent 5-tap stride-1 convolution over the
+    8*Cin space-to-depth channels, packed per stage: [5 z-tap][Cin chunk][25 taps][2][npad/8][8][4].
+    Input index 2(o+delta)+pi = 2o - 3 + k  =>  k = 2 delta + 3 + pi, delta = 2 - t (kernel: input = j + 2 - t)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    t5 = 5
+    weq = weight.new_zeros((cin, 2, 2, 2, npad, t5, t5, t5))   # (ci, pz, py, px, n, tz, ty, tx)
+    for pz in (0, 1):
+        for py in (0, 1):
+            for px in (0, 1):
+                for tz in range(t5):
+                    kz = 2 * (2 - tz) + 3 + pz
+                    if not 0 <= kz < 8:
+                        continue
+                    for ty in range(t5):
+                        ky = 2 * (2 - ty) + 3 + py
+                        if not 0 <= ky < 8:
+                            continue
+                        for tx in range(t5):
+                            kx = 2 * (2 - tx) + 3 + px
+                            if 0 <= kx < 8:
+                                weq[:, pz, py, px, :cout, tz, ty, tx] = weight[:, :, kz, ky, kx].t()
+    ceq = cin * 8
+    sub = weq.reshape(ceq // 8, 2, 4, npad // 8, 8, t5, t5, t5)            # (kc, kk, e, ng, r, tz, ty, tx)
+    return sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()               # (tz, kc, ty, tx, kk, ng, r, e)
+
+
+def _packed_conv(module, npad):
+    w = module.weight
+    key = (id(module), npad, "k8s2")
+    ver = (w._version, w.data_ptr(), w.device)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, pack_conv_k8s2_weights(w.detach(), npad))
+        _wcache[key] = hit
+    return hit[1]
+
+
+def _conv_k8s2_supported(x, m):
+    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and tuple(m.kernel_size) == (8, 8, 8)
+            and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (3, 3, 3) and tuple(m.dilation) == (1, 1, 1)
+            and m.groups == 1 and m.out_channels <= 32 and x.shape[1] % 2 == 0 and x.shape[1] <= 8
+            and all(v % 2 == 0 for v in x.shape[2:]) and x.shape[4] // 2 in (16, 32, 64) and (x.shape[3] // 2) % 16 == 0
+            and m.padding_mode == "zeros")
+
+
+def conv3d(x, m, bn=None, slope=None):
+    """Conv3d(k=8, s=2, p=3) on few input channels (Unet_3D.enc1) [+ folded eval BatchNorm3d + LeakyReLU]."""
+    if not (_conv_k8s2_supported(x, m) and _no_autograd(x, m.weight, m.bias)):
+        return None
+    cout, npad = m.out_channels, 32
+    scale = shift = None
+    if bn is not None:
+        if bn.training or not bn.track_running_stats:
+            return None
+        inv = torch.rsqrt(bn.running_var + bn.eps)
+        scale = inv * (bn.weight if bn.weight is not None else 1.0)
+        bias = m.bias.detach() if m.bias is not None else torch.zeros_like(bn.running_mean)
+        shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
+    dev = x.device
+    sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
+    if shift is None:
+        shift = m.bias.detach() if m.bias is not None else torch.zeros(cout, device=dev)
+    sh = torch.nn.functional.pad(shift.float(), (0, npad - cout))
+    xb = space_to_depth_blocked(x)
+    b = x.shape[0]
+    bd, cg, h, w, _ = xb.shape
+    cgo = (cout + 3) // 4
+    out = torch.empty((bd, cgo, h, w, 4), device=dev, dtype=torch.float32)
+    _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg, None, 0, b, bd // b, h, w,
+              _packed_conv(m, npad).data_ptr(), 5, 2, npad, sc.data_ptr(), sh.data_ptr(),
+              1.0 if slope is None else float(slope), out.data_ptr(), cgo, _lib.stream_ptr(x))
+    return from_blocked(out, b, cout)
 
 
 def conv_transpose3d(x, m):

@@ -185,6 +185,17 @@ int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const float *src1,
                                   const float *scale, const float *shift, float slope,
                                   float *out, int cgo, void *stream);
 
+/* Stride-1 convolution with `taps` (3 or 5) taps per dimension on channel-blocked activations, same tcgen05 kernel:
+ *   out[b,z,y,x,n] = act(scale[n] * sum_{t,c} in[b, z+base-tz, y+base-ty, x+base-tx, c] * W[t][c][n] + shift[n])
+ * Replaces the cuDNN call behind nn.Conv3d of Unet_3D.enc1 (networks/networks.py:151,197: Conv3d(2->20, k=8, s=2, p=3))
+ * after a space-to-depth of the input (k=8/s=2 over C channels == 5 taps/s=1 over 8C channels).
+ *   wpack [taps][C/8][taps*taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4];  W in {16,32,64}, H % 16 == 0, npad = 32 */
+int genre_b200_conv3d_taps_forward(const float *src0, int cg0, const float *src1, int cg1,
+                                   int64_t B, int64_t D, int64_t H, int64_t W,
+                                   const float *wpack, int taps, int base, int npad,
+                                   const float *scale, const float *shift, float slope,
+                                   float *out, int cgo, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Timing of the tcgen05 ConvTranspose3d kernel against cuDNN on a B200 (CUDA events).  One JSON line.
+    python profiles/microbench_conv.py > gpurun_out/microbench_conv.json
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import genre_shapehd_b200  # noqa: E402
+
+genre_shapehd_b200.install()
+from genre_shapehd_b200 import ops_conv  # noqa: E402
+import networks.networks as nets  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.cuda.set_device(dev)
+B = int(os.environ.get("B", 16))
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps  # ms
+
+
+out = {"B": B}
+layers = {"unet_dec5": (80, 20, 8, 32), "unet_dec4": (160, 40, 4, 16), "voxdec5": (64, 32, 4, 32), "gen5": (64, 64, 4, 32),
+          "voxdec4": (128, 64, 4, 16)}
+with torch.no_grad():
+    for name, (cin, cout, k, s) in layers.items():
+        m = nets.ConvTranspose3d(cin, cout, k, 2, k // 2 - 1).to(dev)
+        x = torch.randn(B, cin, s, s, s, device=dev)
+        xb = ops_conv.to_blocked(x)
+        flop = 2.0 * B * (2 * s) ** 3 * cout * cin * (k // 2) ** 3
+        t_kernel = timeit(lambda: ops_conv.convt3d_s2_blocked(xb, None, B, m))
+        t_total = timeit(lambda: ops_conv.conv_transpose3d(x, m))
+        torch.backends.cudnn.allow_tf32 = True
+        t_cudnn_tf32 = timeit(lambda: F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding))
+        torch.backends.cudnn.allow_tf32 = False
+        t_cudnn_fp32 = timeit(lambda: F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding))
+        out[name] = {"gflop": flop / 1e9, "kernel_ms": t_kernel, "kernel_tflops": flop / t_kernel / 1e9,
+                     "with_layout_conversion_ms": t_total, "cudnn_tf32_ms": t_cudnn_tf32, "cudnn_fp32_ms": t_cudnn_fp32}
+    # whole refiner, eval mode
+    net = nets.Unet_3D().to(dev).eval()
+    x = torch.rand(B, 2, 128, 128, 128, device=dev)
+    torch.backends.cudnn.allow_tf32 = True
+    ops_conv.ENABLED = True
+    out["unet3d_eval_custom_ms"] = timeit(lambda: net(x), reps=5, warm=2)
+    ops_conv.ENABLED = False
+    out["unet3d_eval_cudnn_tf32_ms"] = timeit(lambda: net(x), reps=5, warm=2)
+    torch.backends.cudnn.allow_tf32 = False
+    out["unet3d_eval_cudnn_fp32_ms"] = timeit(lambda: net(x), reps=5, warm=2)
+print(json.dumps(out))

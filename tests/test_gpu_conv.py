@@ -10,9 +10,19 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _tf32_on():
+    torch.backends.cudnn.allow_tf32 = True   # the custom kernels are TF32: they decline when TF32 is disallowed
+    yield
+    torch.backends.cudnn.allow_tf32 = True
+
+
 def _ref(x, m):
     torch.backends.cudnn.allow_tf32 = False
-    return F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding)
+    try:
+        return F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding)
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
 
 
 @pytest.mark.parametrize("k,cin,cout,b,d,h,w", [(4, 8, 4, 1, 1, 16, 16), (8, 8, 20, 1, 2, 16, 16), (8, 80, 20, 2, 4, 32, 32),
@@ -48,6 +58,7 @@ def test_deconv_skip_fused_bn_leaky_vs_torch():
         y = blk(x, s)
         torch.backends.cudnn.allow_tf32 = False
         ref = blk.net(torch.cat((x, s), 1))
+        torch.backends.cudnn.allow_tf32 = True
     assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
 
@@ -60,3 +71,42 @@ def test_autograd_and_unsupported_shapes_fall_back():
     assert x.grad is not None
     with torch.no_grad():
         assert ops_conv.conv_transpose3d(torch.randn(1, 8, 2, 8, 8, device=DEV), m) is None   # W=8 not covered
+
+
+@pytest.mark.parametrize("cin,cout,b,d,h,w", [(2, 20, 1, 4, 32, 32), (2, 20, 2, 8, 64, 64), (4, 12, 1, 6, 32, 128)])
+def test_conv3d_k8s2_via_space_to_depth_vs_torch(cin, cout, b, d, h, w):
+    torch.manual_seed(cin * 100 + cout + w)
+    m = nets.Conv3d(cin, cout, 8, 2, 3).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV)
+    with torch.no_grad():
+        y = ops_conv.conv3d(x, m)
+        assert y is not None
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=3)
+        torch.backends.cudnn.allow_tf32 = True
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+def test_conv_block_fused_bn_leaky_vs_torch():
+    torch.manual_seed(11)
+    blk = nets.Conv3d_block(2, 20, 8, 2, 3).to(DEV).eval()
+    blk.net[1].running_mean.normal_(0, 0.1)
+    blk.net[1].running_var.uniform_(0.5, 1.5)
+    x = torch.rand(1, 2, 8, 64, 64, device=DEV)
+    with torch.no_grad():
+        y = blk(x)
+        torch.backends.cudnn.allow_tf32 = False
+        ref = blk.net(x)
+        torch.backends.cudnn.allow_tf32 = True
+    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+def test_tf32_switch_is_honoured():
+    m = nets.ConvTranspose3d(8, 4, 4, 2, 1).to(DEV)
+    x = torch.randn(1, 8, 2, 16, 16, device=DEV)
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        assert ops_conv.conv_transpose3d(x, m) is None     # fp32 requested: the cuDNN fp32 path runs instead
+        torch.backends.cudnn.allow_tf32 = True
+        assert ops_conv.conv_transpose3d(x, m) is not None
