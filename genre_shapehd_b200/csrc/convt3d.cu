@@ -30,7 +30,8 @@ constexpr int CT_BY = 16;             // y rows per CTA (16 core-matrix groups o
 constexpr int CT_KCG = 2;             // channel groups (of 4) per stage = one K=8 TF32 MMA per tap and M-tile
 
 struct ConvTParams {
-  const float *src0, *src1;  // blocked activations [B*D][cg][H][W][4]; src1 may be null (cg1 = 0)
+  const float *src0, *src1;  // blocked activations [B*D][cg][H][W][16 bytes]; src1 may be null (cg1 = 0).
+                             // A channel group is 16 bytes per position: 4 fp32 (TF32 path) or 8 fp16 (F16 path).
   int cg0, cg1;
   int B, D, H, W;            // input extent
   const float *wpack;        // [8 parity][T ztap][nchunk][T*T taps][2 kcore][NPAD/8][8][4]
@@ -104,6 +105,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// kind::f16 with fp16 operands (format 0), fp32 accumulate: K = 16 per instruction
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -146,7 +159,7 @@ struct ConvTCfg {
 
 // PAR = true : 8 parity classes (blockIdx.y), output at 2*j + parity (ConvTranspose3d stride 2)
 // PAR = false: one class, output at j (stride-1 tap convolution; strided Conv3d arrives here after space-to-depth)
-template <int T, int NPAD, int MT, bool PAR>
+template <int T, int NPAD, int MT, bool PAR, bool F16>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 convt3d_s2_kernel(const ConvTParams p) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
@@ -279,7 +292,7 @@ convt3d_s2_kernel(const ConvTParams p) {
     tc_fence_before();
   } else if (lane == 0) {
     // ===================== MMA issuer (one thread) =============================================================
-    constexpr uint32_t idesc = umma_idesc_tf32(128, NPAD);
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, NPAD) : umma_idesc_tf32(128, NPAD);
     bool first = true;
     for (int it = 0; it < n_stages_total; ++it) {
       const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
@@ -296,7 +309,9 @@ convt3d_s2_kernel(const ConvTParams p) {
           for (int mt = 0; mt < MT; ++mt) {
             // rows of this M-tile under tap (ty,tx): halo row (T-1-ty) + y, column (T-1-tx) + 8*mt + x
             const uint32_t a0 = sa + (((T - 1 - ty) * Cfg::PX) + (T - 1 - tx) + 8 * mt) * 16;
-            umma_tf32(tmem_base + mt * NPAD, umma_desc(a0, Cfg::A_CG_BYTES, Cfg::PX * 16), bdesc, idesc, !first || (ty | tx));
+            const uint64_t adesc = umma_desc(a0, Cfg::A_CG_BYTES, Cfg::PX * 16);
+            if (F16) umma_f16(tmem_base + mt * NPAD, adesc, bdesc, idesc, !first || (ty | tx));
+            else umma_tf32(tmem_base + mt * NPAD, adesc, bdesc, idesc, !first || (ty | tx));
           }
         }
       }
@@ -315,10 +330,10 @@ convt3d_s2_kernel(const ConvTParams p) {
   }
 }
 
-template <int T, int NPAD, int MT, bool PAR>
-static int launch_convt(const ConvTParams &p, cudaStream_t st) {
+template <int T, int NPAD, int MT, bool PAR, bool F16>
+static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
-  auto kern = convt3d_s2_kernel<T, NPAD, MT, PAR>;
+  auto kern = convt3d_s2_kernel<T, NPAD, MT, PAR, F16>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -335,6 +350,12 @@ static int launch_convt(const ConvTParams &p, cudaStream_t st) {
   return check_launch("convt3d_s2 kernel");
 }
 
+static thread_local bool g_conv_f16 = false;  // operand type of the next launch (set by the C ABI entry points)
+template <int T, int NPAD, int MT, bool PAR>
+static int launch_convt(const ConvTParams &p, cudaStream_t st) {
+  return g_conv_f16 ? launch_convt_impl<T, NPAD, MT, PAR, true>(p, st) : launch_convt_impl<T, NPAD, MT, PAR, false>(p, st);
+}
+
 }  // namespace gb
 
 using namespace gb;
@@ -345,10 +366,12 @@ using namespace gb;
 //   scale, shift [npad]: per-channel affine applied to the accumulator (bias and folded eval-mode BatchNorm),
 //   slope: LeakyReLU slope (1 = none).   out [B*2D][cgo][2H][2W][4]
 // Supported: W in {16, 32}, H % 16 == 0, (cg0 + cg1) even, cg0 even, 4*cgo <= npad, npad in {32, 64}.
-extern "C" int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const float *src1, int cg1, int64_t B,
-                                             int64_t D, int64_t H, int64_t W, const float *wpack, int ksize, int npad,
-                                             const float *scale, const float *shift, float slope, float *out, int cgo,
-                                             void *stream) {
+extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
+                                             int64_t D, int64_t H, int64_t W, const void *wpack_, int ksize, int npad,
+                                             int f16, const float *scale, const float *shift, float slope, float *out,
+                                             int cgo, void *stream) {
+  const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
+  g_conv_f16 = f16 != 0;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "convt3d: null pointer");
   GB_REQUIRE(ksize == 4 || ksize == 8, GENRE_B200_EINVAL, "convt3d: kernel size %d unsupported (4 or 8)", ksize);
   GB_REQUIRE(npad == 32 || npad == 64, GENRE_B200_EINVAL, "convt3d: npad %d unsupported (32 or 64)", npad);
@@ -390,10 +413,12 @@ extern "C" int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const f
 // Conv3d(2 -> 20, k=8, s=2, p=3) (networks/networks.py:151) is a 5-tap stride-1 convolution over the 16 s2d channels.
 //   wpack [T z-tap][C/8 chunk][T*T taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4]
 // Supported: T in {3, 5}, W in {16, 32, 64}, H % 16 == 0, npad = 32.
-extern "C" int genre_b200_conv3d_taps_forward(const float *src0, int cg0, const float *src1, int cg1, int64_t B,
-                                              int64_t D, int64_t H, int64_t W, const float *wpack, int taps, int base,
-                                              int npad, const float *scale, const float *shift, float slope,
+extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
+                                              int64_t D, int64_t H, int64_t W, const void *wpack_, int taps, int base,
+                                              int npad, int f16, const float *scale, const float *shift, float slope,
                                               float *out, int cgo, void *stream) {
+  const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
+  g_conv_f16 = f16 != 0;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_taps: null pointer");
   GB_REQUIRE(taps == 3 || taps == 5, GENRE_B200_EINVAL, "conv3d_taps: %d taps unsupported (3 or 5)", taps);
   GB_REQUIRE(npad == 32, GENRE_B200_EINVAL, "conv3d_taps: npad %d unsupported (32)", npad);

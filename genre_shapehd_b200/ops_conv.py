@@ -19,13 +19,32 @@ import torch
 from . import _lib
 
 ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
+# Operand type of the tensor-core kernels: "f16" (default) = fp16 operands, fp32 accumulation: the same 10-bit
+# mantissa as TF32 with half the operand bytes (the kernels are bound by shared-memory operand bandwidth, so ~2x
+# faster); "tf32" = fp32 storage read as TF32.  Both accumulate in fp32 and produce fp32 activations.
+PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "f16")
 _wcache = {}
 
 
-def to_blocked(x):
-    """NCDHW [B,C,D,H,W] (C % 4 == 0) -> [B*D, C/4, H, W, 4] contiguous."""
+def _f16():
+    return PRECISION == "f16"
+
+
+def _group():
+    """channels per 16-byte channel group"""
+    return 8 if _f16() else 4
+
+
+def to_blocked(x, group=4, dtype=None):
+    """NCDHW [B,C,D,H,W] (C % group == 0) -> [B*D, C/group, H, W, group] contiguous (optionally cast)."""
     b, c, d, h, w = x.shape
-    return x.reshape(b, c // 4, 4, d, h, w).permute(0, 3, 1, 4, 5, 2).contiguous().view(b * d, c // 4, h, w, 4)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x.reshape(b, c // group, group, d, h, w).permute(0, 3, 1, 4, 5, 2).contiguous().view(b * d, c // group, h, w, group)
+
+
+def _to_operand(x):
+    return to_blocked(x, 8, torch.float16) if _f16() else to_blocked(x, 4)
 
 
 def from_blocked(y, batch, channels):
@@ -35,31 +54,34 @@ def from_blocked(y, batch, channels):
     return y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
 
 
-def pack_convt_weights(weight, npad):
+def pack_convt_weights(weight, npad, group=4):
     """ConvTranspose3d weight [Cin, Cout, K, K, K] -> the per-stage shared-memory images the kernel bulk-copies:
-    [8 parity][T z-tap][Cin/8 chunk][T*T (y,x) taps][2 k-core][npad/8 n-group][8 n][4 k]  (T = K/2)."""
+    [8 parity][T z-tap][Cin/(2g) chunk][T*T (y,x) taps][2 k-core][npad/8 n-group][8 n][g k]  (T = K/2; g = 4 fp32
+    or 8 fp16 elements per 16-byte core-matrix row)."""
     cin, cout, k = weight.shape[0], weight.shape[1], weight.shape[2]
     t, pad = k // 2, k // 2 - 1
+    g = group
     k0 = [(p + pad) % 2 for p in (0, 1)]
     wp = weight.new_zeros((cin, npad, k, k, k))
     wp[:, :cout] = weight
-    out = weight.new_empty((2, 2, 2, t, cin // 8, t, t, 2, npad // 8, 8, 4))
+    out = weight.new_empty((2, 2, 2, t, cin // (2 * g), t, t, 2, npad // 8, 8, g))
     for pz in (0, 1):
         for py in (0, 1):
             for px in (0, 1):
                 sub = wp[:, :, k0[pz]::2, k0[py]::2, k0[px]::2]                      # [Cin, npad, tz, ty, tx]
-                sub = sub.reshape(cin // 8, 2, 4, npad // 8, 8, t, t, t)              # (kc, kk, e, ng, r, tz, ty, tx)
+                sub = sub.reshape(cin // (2 * g), 2, g, npad // 8, 8, t, t, t)        # (kc, kk, e, ng, r, tz, ty, tx)
                 out[pz, py, px] = sub.permute(5, 0, 6, 7, 1, 3, 4, 2)                 # (tz, kc, ty, tx, kk, ng, r, e)
-    return out.contiguous()
+    out = out.contiguous()
+    return out.half() if g == 8 else out
 
 
 def _packed(module, npad):
     w = module.weight
-    key = (id(module), npad)
+    key = (id(module), npad, _group())
     ver = (w._version, w.data_ptr(), w.device)
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
-        hit = (ver, pack_convt_weights(w.detach(), npad))
+        hit = (ver, pack_convt_weights(w.detach(), npad, _group()))
         _wcache[key] = hit
     return hit[1]
 
@@ -70,11 +92,12 @@ def _convt_supported(shape_bcdhw, module):
     return (ENABLED and tuple(module.kernel_size) == (k, k, k) and k in (4, 8) and tuple(module.stride) == (2, 2, 2)
             and tuple(module.padding) == (k // 2 - 1,) * 3 and tuple(module.output_padding) == (0, 0, 0)
             and tuple(module.dilation) == (1, 1, 1) and module.groups == 1 and w in (16, 32) and h % 16 == 0
-            and c % 8 == 0 and module.out_channels <= 64)
+            and c % (2 * _group()) == 0 and module.out_channels <= 64)
 
 
 def convt3d_s2_blocked(src0, src1, batch, module, scale=None, shift=None, slope=1.0):
-    """Run the kernel on blocked inputs; returns the blocked output [B*2D, cgo, 2H, 2W, 4]."""
+    """Run the kernel on blocked operands (fp32 groups of 4 or fp16 groups of 8, matching PRECISION); returns the
+    blocked fp32 output [B*2D, cgo, 2H, 2W, 4]."""
     bd, cg0, h, w, _ = src0.shape
     cg1 = src1.shape[1] if src1 is not None else 0
     cout = module.out_channels
@@ -88,8 +111,8 @@ def convt3d_s2_blocked(src0, src1, batch, module, scale=None, shift=None, slope=
     sh = torch.nn.functional.pad(shift.float(), (0, npad - cout))
     out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=dev, dtype=torch.float32)
     _lib.call("genre_b200_convt3d_s2_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None, cg1,
-              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, sc.data_ptr(), sh.data_ptr(),
-              float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
+              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, 1 if src0.dtype == torch.float16 else 0,
+              sc.data_ptr(), sh.data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
     return out
 
 
@@ -101,16 +124,18 @@ def _no_autograd(*tensors):
     return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
 
-def space_to_depth_blocked(x):
-    """NCDHW [B,C,D,H,W] (even extents, C*8 % 4 == 0) -> blocked [B*D/2, C*8/4, H/2, W/2, 4] whose channel index is
-    ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px)."""
+def space_to_depth_blocked(x, group=4, dtype=None):
+    """NCDHW [B,C,D,H,W] (even extents, C*8 % group == 0) -> blocked [B*D/2, C*8/group, H/2, W/2, group] whose channel
+    index is ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px)."""
     b, c, d, h, w = x.shape
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
     t = x.reshape(b, c, d // 2, 2, h // 2, 2, w // 2, 2).permute(0, 2, 1, 3, 5, 7, 4, 6)   # b z' c pz py px y' x'
-    t = t.reshape(b * (d // 2), (c * 8) // 4, 4, h // 2, w // 2).permute(0, 1, 3, 4, 2)
+    t = t.reshape(b * (d // 2), (c * 8) // group, group, h // 2, w // 2).permute(0, 1, 3, 4, 2)
     return t.contiguous()
 
 
-def pack_conv_k8s2_weights(weight, npad):
+def pack_conv_k8s2_weights(weight, npad, group=4):
     """Conv3d weight [Cout, Cin, 8, 8, 8] (stride 2, padding 3) -> the equivalent 5-tap stride-1 convolution over the
     8*Cin space-to-depth channels, packed per stage: [5 z-tap][Cin chunk][25 taps][2][npad/8][8][4].
     Input index 2(o+delta)+pi = 2o - 3 + k  =>  k = 2 delta + 3 + pi, delta = 2 - t (kernel: input = j + 2 - t)."""
@@ -132,18 +157,19 @@ def pack_conv_k8s2_weights(weight, npad):
                             kx = 2 * (2 - tx) + 3 + px
                             if 0 <= kx < 8:
                                 weq[:, pz, py, px, :cout, tz, ty, tx] = weight[:, :, kz, ky, kx].t()
-    ceq = cin * 8
-    sub = weq.reshape(ceq // 8, 2, 4, npad // 8, 8, t5, t5, t5)            # (kc, kk, e, ng, r, tz, ty, tx)
-    return sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()               # (tz, kc, ty, tx, kk, ng, r, e)
+    ceq, g = cin * 8, group
+    sub = weq.reshape(ceq // (2 * g), 2, g, npad // 8, 8, t5, t5, t5)      # (kc, kk, e, ng, r, tz, ty, tx)
+    out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                # (tz, kc, ty, tx, kk, ng, r, e)
+    return out.half() if g == 8 else out
 
 
 def _packed_conv(module, npad):
     w = module.weight
-    key = (id(module), npad, "k8s2")
+    key = (id(module), npad, "k8s2", _group())
     ver = (w._version, w.data_ptr(), w.device)
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
-        hit = (ver, pack_conv_k8s2_weights(w.detach(), npad))
+        hit = (ver, pack_conv_k8s2_weights(w.detach(), npad, _group()))
         _wcache[key] = hit
     return hit[1]
 
@@ -174,13 +200,13 @@ def conv3d(x, m, bn=None, slope=None):
     if shift is None:
         shift = m.bias.detach() if m.bias is not None else torch.zeros(cout, device=dev)
     sh = torch.nn.functional.pad(shift.float(), (0, npad - cout))
-    xb = space_to_depth_blocked(x)
+    xb = space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x)
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
     cgo = (cout + 3) // 4
     out = torch.empty((bd, cgo, h, w, 4), device=dev, dtype=torch.float32)
     _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg, None, 0, b, bd // b, h, w,
-              _packed_conv(m, npad).data_ptr(), 5, 2, npad, sc.data_ptr(), sh.data_ptr(),
+              _packed_conv(m, npad).data_ptr(), 5, 2, npad, 1 if _f16() else 0, sc.data_ptr(), sh.data_ptr(),
               1.0 if slope is None else float(slope), out.data_ptr(), cgo, _lib.stream_ptr(x))
     return from_blocked(out, b, cout)
 
@@ -189,7 +215,7 @@ def conv_transpose3d(x, m):
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_supported(x.shape, m)
             and _no_autograd(x, m.weight, m.bias)):
         return None
-    y = convt3d_s2_blocked(to_blocked(x), None, x.shape[0], m)
+    y = convt3d_s2_blocked(_to_operand(x), None, x.shape[0], m)
     return from_blocked(y, x.shape[0], m.out_channels)
 
 
@@ -197,7 +223,7 @@ def deconv_skip(x, skip, conv, bn=None, slope=None):
     """cat(x, skip) -> ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> LeakyReLU(slope)] with the
     concatenation walked as two K ranges instead of being materialised.  None if not covered."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
-            and x.shape[1] % 8 == 0 and skip.shape[1] % 8 == 0
+            and x.shape[1] % _group() == 0 and skip.shape[1] % _group() == 0
             and _convt_supported((x.shape[0], x.shape[1] + skip.shape[1]) + tuple(x.shape[2:]), conv)
             and _no_autograd(x, skip, conv.weight, conv.bias)):
         return None
@@ -209,6 +235,11 @@ def deconv_skip(x, skip, conv, bn=None, slope=None):
         scale = inv * (bn.weight if bn.weight is not None else 1.0)
         bias = conv.bias.detach() if conv.bias is not None else torch.zeros_like(bn.running_mean)
         shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
-    y = convt3d_s2_blocked(to_blocked(x), to_blocked(skip), x.shape[0], conv, scale, shift,
-                           1.0 if slope is None else slope)
+    g2 = 2 * _group()
+    if x.shape[1] % g2 == 0 and skip.shape[1] % g2 == 0:
+        a, bsrc = _to_operand(x), _to_operand(skip)          # the concatenation stays two K ranges
+    else:
+        # a K chunk (2 channel groups) may not straddle the two tensors: join them in the blocked domain instead
+        a, bsrc = torch.cat((_to_operand(x), _to_operand(skip)), dim=1), None
+    y = convt3d_s2_blocked(a, bsrc, x.shape[0], conv, scale, shift, 1.0 if slope is None else slope)
     return from_blocked(y, x.shape[0], conv.out_channels)

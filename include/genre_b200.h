@@ -173,15 +173,17 @@ int genre_b200_voxelize_stage_splat(int64_t n_maps, int64_t pixels_per_map, int 
  * FP32 accumulation in TMEM).  Replaces the cuDNN call behind nn.ConvTranspose3d in networks/networks.py:211-222
  * (Unet_3D Deconv3d_skip: the channel concatenation of :221 is walked as two K ranges, never materialised) and
  * :253-256 (deconv3d_2x of VoxelDecoder / VoxelGenerator).
- *   src0 [B*D][cg0][H][W][4], src1 [B*D][cg1][H][W][4] or NULL   channel-blocked activations (cg = channels/4)
+ *   src0 [B*D][cg0][H][W][16 B], src1 [...] or NULL   channel-blocked activations; a channel group is 16 bytes per
+ *           position: 4 fp32 read as TF32 (f16 = 0) or 8 fp16 (f16 = 1; same 10-bit mantissa, half the operand bytes:
+ *           the kernels are bound by shared-memory operand bandwidth, so this path is ~2x faster)
  *   wpack   weights packed per (parity, z-tap, 8-channel chunk) stage: see genre_shapehd_b200/ops_conv.py
  *   scale, shift [npad]   y = act(acc * scale + shift): bias and folded eval-mode BatchNorm3d
  *   slope   LeakyReLU slope (1 = none);   out [B*2D][cgo][2H][2W][4]
  * Supported: W in {16,32}, H % 16 == 0, cg0, cg1 even, 4*cgo <= npad, npad in {32,64}.
  * ------------------------------------------------------------------------------------------- */
-int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const float *src1, int cg1,
+int genre_b200_convt3d_s2_forward(const void *src0, int cg0, const void *src1, int cg1,
                                   int64_t B, int64_t D, int64_t H, int64_t W,
-                                  const float *wpack, int ksize, int npad,
+                                  const void *wpack, int ksize, int npad, int f16,
                                   const float *scale, const float *shift, float slope,
                                   float *out, int cgo, void *stream);
 
@@ -190,9 +192,9 @@ int genre_b200_convt3d_s2_forward(const float *src0, int cg0, const float *src1,
  * Replaces the cuDNN call behind nn.Conv3d of Unet_3D.enc1 (networks/networks.py:151,197: Conv3d(2->20, k=8, s=2, p=3))
  * after a space-to-depth of the input (k=8/s=2 over C channels == 5 taps/s=1 over 8C channels).
  *   wpack [taps][C/8][taps*taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4];  W in {16,32,64}, H % 16 == 0, npad = 32 */
-int genre_b200_conv3d_taps_forward(const float *src0, int cg0, const float *src1, int cg1,
+int genre_b200_conv3d_taps_forward(const void *src0, int cg0, const void *src1, int cg1,
                                    int64_t B, int64_t D, int64_t H, int64_t W,
-                                   const float *wpack, int taps, int base, int npad,
+                                   const void *wpack, int taps, int base, int npad, int f16,
                                    const float *scale, const float *shift, float slope,
                                    float *out, int cgo, void *stream);
 

@@ -35,16 +35,17 @@ def timeit(fn, reps=10, warm=3):
     return e0.elapsed_time(e1) / reps  # ms
 
 
-out = {"B": B}
+out = {"B": B, "precision": ops_conv.PRECISION}
 layers = {"unet_dec5": (80, 20, 8, 32), "unet_dec4": (160, 40, 4, 16), "voxdec5": (64, 32, 4, 32), "gen5": (64, 64, 4, 32),
           "voxdec4": (128, 64, 4, 16)}
 with torch.no_grad():
     for name, (cin, cout, k, s) in layers.items():
         m = nets.ConvTranspose3d(cin, cout, k, 2, k // 2 - 1).to(dev)
         x = torch.randn(B, cin, s, s, s, device=dev)
-        xb = ops_conv.to_blocked(x)
+        xb = ops_conv._to_operand(x)
         flop = 2.0 * B * (2 * s) ** 3 * cout * cin * (k // 2) ** 3
         t_kernel = timeit(lambda: ops_conv.convt3d_s2_blocked(xb, None, B, m))
+        torch.backends.cudnn.allow_tf32 = True
         t_total = timeit(lambda: ops_conv.conv_transpose3d(x, m))
         torch.backends.cudnn.allow_tf32 = True
         t_cudnn_tf32 = timeit(lambda: F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding))

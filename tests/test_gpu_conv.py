@@ -10,10 +10,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(autouse=True)
-def _tf32_on():
-    torch.backends.cudnn.allow_tf32 = True   # the custom kernels are TF32: they decline when TF32 is disallowed
+@pytest.fixture(autouse=True, params=["f16", "tf32"])
+def _precision(request):
+    """every test runs with both operand types of the tensor-core kernels"""
+    torch.backends.cudnn.allow_tf32 = True   # the custom kernels decline when reduced-mantissa convolutions are disallowed
+    old = ops_conv.PRECISION
+    ops_conv.PRECISION = request.param
     yield
+    ops_conv.PRECISION = old
     torch.backends.cudnn.allow_tf32 = True
 
 
@@ -25,8 +29,8 @@ def _ref(x, m):
         torch.backends.cudnn.allow_tf32 = True
 
 
-@pytest.mark.parametrize("k,cin,cout,b,d,h,w", [(4, 8, 4, 1, 1, 16, 16), (8, 8, 20, 1, 2, 16, 16), (8, 80, 20, 2, 4, 32, 32),
-                                                 (4, 64, 32, 1, 3, 32, 32), (4, 128, 64, 2, 2, 16, 16), (8, 16, 40, 1, 2, 32, 16)])
+@pytest.mark.parametrize("k,cin,cout,b,d,h,w", [(4, 16, 4, 1, 1, 16, 16), (8, 16, 20, 1, 2, 16, 16), (8, 80, 20, 2, 4, 32, 32),
+                                                 (4, 64, 32, 1, 3, 32, 32), (4, 128, 64, 2, 2, 16, 16), (8, 32, 40, 1, 2, 32, 16)])
 def test_convt3d_vs_torch(k, cin, cout, b, d, h, w):
     torch.manual_seed(k * 1000 + cin + cout)
     m = nets.ConvTranspose3d(cin, cout, k, 2, k // 2 - 1).to(DEV)
@@ -44,6 +48,7 @@ def test_convt3d_vs_torch(k, cin, cout, b, d, h, w):
 def test_blocked_layout_roundtrip():
     x = torch.randn(2, 24, 3, 16, 16, device=DEV)
     assert torch.equal(ops_conv.from_blocked(ops_conv.to_blocked(x), 2, 24), x)
+    assert ops_conv.to_blocked(x, 8, torch.float16).shape == (6, 3, 16, 16, 8)
 
 
 def test_deconv_skip_fused_bn_leaky_vs_torch():
@@ -63,14 +68,14 @@ def test_deconv_skip_fused_bn_leaky_vs_torch():
 
 
 def test_autograd_and_unsupported_shapes_fall_back():
-    m = nets.ConvTranspose3d(8, 4, 4, 2, 1).to(DEV)
-    x = torch.randn(1, 8, 2, 16, 16, device=DEV, requires_grad=True)
+    m = nets.ConvTranspose3d(16, 4, 4, 2, 1).to(DEV)
+    x = torch.randn(1, 16, 2, 16, 16, device=DEV, requires_grad=True)
     assert ops_conv.conv_transpose3d(x, m) is None             # autograd: cuDNN path
     y = m(x)
     y.sum().backward()
     assert x.grad is not None
     with torch.no_grad():
-        assert ops_conv.conv_transpose3d(torch.randn(1, 8, 2, 8, 8, device=DEV), m) is None   # W=8 not covered
+        assert ops_conv.conv_transpose3d(torch.randn(1, 16, 2, 8, 8, device=DEV), m) is None   # W=8 not covered
 
 
 @pytest.mark.parametrize("cin,cout,b,d,h,w", [(2, 20, 1, 4, 32, 32), (2, 20, 2, 8, 64, 64), (4, 12, 1, 6, 32, 128)])
@@ -103,8 +108,8 @@ def test_conv_block_fused_bn_leaky_vs_torch():
 
 
 def test_tf32_switch_is_honoured():
-    m = nets.ConvTranspose3d(8, 4, 4, 2, 1).to(DEV)
-    x = torch.randn(1, 8, 2, 16, 16, device=DEV)
+    m = nets.ConvTranspose3d(16, 4, 4, 2, 1).to(DEV)
+    x = torch.randn(1, 16, 2, 16, 16, device=DEV)
     with torch.no_grad():
         torch.backends.cudnn.allow_tf32 = False
         assert ops_conv.conv_transpose3d(x, m) is None     # fp32 requested: the cuDNN fp32 path runs instead
