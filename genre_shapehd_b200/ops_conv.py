@@ -48,10 +48,22 @@ def _to_operand(x):
 
 
 def from_blocked(y, batch, channels):
-    """[B*D, cg, H, W, 4] -> NCDHW [B, channels, D, H, W] (drops channel padding)."""
+    """[B*D, cg, H, W, 4] -> NCDHW [B, channels, D, H, W] (drops channel padding).  The blocked tensor stays attached to
+    the result so that a following custom layer can consume it without converting back."""
     bd, cg, h, w, _ = y.shape
     d = bd // batch
-    return y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
+    out = y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
+    out._gb_blocked = y
+    return out
+
+
+def _blocked_f32(x):
+    """fp32 group-of-4 blocked view of an NCDHW tensor: the cached one if x came out of a custom layer"""
+    y = getattr(x, "_gb_blocked", None)
+    if y is not None and y.shape[1] * 4 >= x.shape[1] and y.shape[0] == x.shape[0] * x.shape[2] \
+            and (y.shape[1] - 1) * 4 < x.shape[1] + 4 and x.shape[1] % 4 == 0:
+        return y
+    return to_blocked(x, 4)
 
 
 def pack_convt_weights(weight, npad, group=4):
@@ -211,7 +223,29 @@ def conv3d(x, m, bn=None, slope=None):
     return from_blocked(out, b, cout)
 
 
+def _convt_c1_supported(cin, shape_dhw, m):
+    return (ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1)
+            and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1
+            and m.out_channels == 1 and cin % 4 == 0 and cin <= 192 and shape_dhw[2] % 4 == 0)
+
+
+def convt_c1(src0, src1, batch, m):
+    """ConvTranspose3d(Cin -> 1, k4, s2, p1) on blocked fp32 inputs -> NCDHW [B,1,2D,2H,2W] (csrc/convt_c1.cu)."""
+    bd, cg0, h, w, _ = src0.shape
+    d = bd // batch
+    out = torch.empty((batch, 1, 2 * d, 2 * h, 2 * w), device=src0.device, dtype=torch.float32)
+    wt = m.weight.detach().reshape(m.in_channels, 64).contiguous()
+    bias = float(m.bias.detach()) if m.bias is not None else 0.0
+    _lib.call("genre_b200_convt_c1_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
+              src1.shape[1] if src1 is not None else 0, batch, d, h, w, wt.data_ptr(), bias, 0, out.data_ptr(),
+              _lib.stream_ptr(src0))
+    return out
+
+
 def conv_transpose3d(x, m):
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_c1_supported(x.shape[1], x.shape[2:], m)
+            and _no_autograd(x, m.weight, m.bias)):
+        return convt_c1(_blocked_f32(x), None, x.shape[0], m)
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_supported(x.shape, m)
             and _no_autograd(x, m.weight, m.bias)):
         return None
@@ -222,6 +256,11 @@ def conv_transpose3d(x, m):
 def deconv_skip(x, skip, conv, bn=None, slope=None):
     """cat(x, skip) -> ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> LeakyReLU(slope)] with the
     concatenation walked as two K ranges instead of being materialised.  None if not covered."""
+    if (bn is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
+            and x.shape[1] % 4 == 0 and skip.shape[1] % 4 == 0
+            and _convt_c1_supported(x.shape[1] + skip.shape[1], x.shape[2:], conv)
+            and _no_autograd(x, skip, conv.weight, conv.bias)):
+        return convt_c1(_blocked_f32(x), _blocked_f32(skip), x.shape[0], conv)
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
             and x.shape[1] % _group() == 0 and skip.shape[1] % _group() == 0
             and _convt_supported((x.shape[0], x.shape[1] + skip.shape[1]) + tuple(x.shape[2:]), conv)

@@ -198,6 +198,14 @@ int genre_b200_conv3d_taps_forward(const void *src0, int cg0, const void *src1, 
                                    const float *scale, const float *shift, float slope,
                                    float *out, int cgo, void *stream);
 
+/* ConvTranspose3d(Cin -> 1, kernel 4, stride 2, padding 1) forward on channel-blocked fp32 inputs (FP32 pipe: with one
+ * output channel there is no GEMM for the tensor cores).  Replaces the cuDNN call behind the last layer of each decoder:
+ * Unet_3D.dec6 (networks/networks.py:167-168, two sources = the skip concatenation), VoxelDecoder main.17 (:57),
+ * VoxelGenerator (:98).   weight [Cin][64] = the module's [Cin,1,4,4,4];  out [B][2D][2H][2W] (NCDHW, C = 1). */
+int genre_b200_convt_c1_forward(const float *src0, int cg0, const float *src1, int cg1,
+                                int64_t B, int64_t D, int64_t H, int64_t W,
+                                const float *weight, float bias, int act_sigmoid, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

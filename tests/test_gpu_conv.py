@@ -115,3 +115,30 @@ def test_tf32_switch_is_honoured():
         assert ops_conv.conv_transpose3d(x, m) is None     # fp32 requested: the cuDNN fp32 path runs instead
         torch.backends.cudnn.allow_tf32 = True
         assert ops_conv.conv_transpose3d(x, m) is not None
+
+
+@pytest.mark.parametrize("cin,b,d,h,w", [(8, 1, 3, 8, 8), (40, 2, 4, 16, 32), (32, 1, 5, 12, 20)])
+def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
+    torch.manual_seed(cin + w)
+    m = nets.ConvTranspose3d(cin, 1, 4, 2, 1).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV)
+    with torch.no_grad():
+        y = ops_conv.conv_transpose3d(x, m)
+        assert y is not None
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=1)
+        torch.backends.cudnn.allow_tf32 = True
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())   # plain fp32 FMAs
+
+
+def test_dec6_two_source_path_vs_torch():
+    torch.manual_seed(3)
+    blk = nets.Deconv3d_skip(40, 1, 4, 2, 1, 0, is_activate=False).to(DEV).eval()
+    x, s = torch.randn(1, 20, 4, 16, 16, device=DEV), torch.randn(1, 20, 4, 16, 16, device=DEV)
+    with torch.no_grad():
+        y = blk(x, s)
+        torch.backends.cudnn.allow_tf32 = False
+        ref = blk.net(torch.cat((x, s), 1))
+        torch.backends.cudnn.allow_tf32 = True
+    assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
