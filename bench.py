@@ -320,6 +320,14 @@ def run_b200(args):
                          "the reference op itself is CUDA-only)" % (n_maps, dt),
                "host_cpus": os.cpu_count()}
 
+    # ---- secondary (rank 0, N=1): the GenRe 3D hot path at batch 16, informational ------------------------------------
+    secondary = None
+    if rank == 0 and world == 1:
+        try:
+            secondary = genre3d_path(torch, dev)
+        except Exception as e:  # informational only: never fail the headline measurement
+            secondary = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,9 +336,44 @@ def run_b200(args):
                         "d2h_bytes_per_step": B * RES ** 3 * 4, "steps": Ke, "ms_per_step": ms_e2e / Ke,
                         "result_checksum": checksum},
                 "gpu_launches": launches, "launch_mode": "cuda_graph" if use_graph else "python",
-                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "secondary": secondary}
         print(json.dumps(line), flush=True)
     dist_util.finalize()
+
+
+def genre3d_path(torch, dev, batch=16, reps=5):
+    """BASELINE configs[2] without the two 2D U-ResNets (out of scope): cam_bp -> render_spherical -> sph_pad ->
+    backproject_spherical glue -> clamp/cat -> Unet_3D (eval), glue lines as in the frozen caller
+    (depth_pred_with_sph_inpaint.py:120-126, genre_full_model.py:120-143)."""
+    from genre_shapehd_b200.synth import bench_depth_batch
+    from toolbox.cam_bp.cam_bp.functions import SphericalBackProjection
+    from toolbox.cam_bp.cam_bp.modules.camera_backprojection_module import Camera_back_projection_layer
+    from toolbox.spherical_proj import gen_sph_grid, render_spherical, sph_pad
+    import networks.networks as nets
+    depth = torch.from_numpy(bench_depth_batch(batch)).to(dev)
+    proj, rend = Camera_back_projection_layer(), render_spherical().to(dev)
+    grid = gen_sph_grid().to(dev).expand(batch, -1, -1, -1, -1)
+    unet = nets.Unet_3D().to(dev).eval()
+
+    def step():
+        pd = proj(depth)
+        sph = sph_pad(rend(torch.clamp(pd * 50, 1e-5, 1 - 1e-5)), 16)
+        df, cnt = SphericalBackProjection.apply(1 - sph[:, :, 16:144, 16:144], grid, 128)
+        ps = (-df + 1 / 128) * 128 * torch.clamp(cnt, 0, 1)
+        return unet(torch.cat((ps, torch.clamp(pd / 50, 1e-5, 1 - 1e-5)), dim=1))
+    with torch.no_grad():
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"what": "GenRe 3D hot path (cam_bp + render_spherical + sph_bp + Unet_3D eval), batch %d, 2D nets excluded" % batch,
+            "ms_per_batch": ms, "shapes_per_s": batch / ms * 1e3}
 
 
 def main():

@@ -63,6 +63,7 @@ cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long lo
                    const float *__restrict__ fl_in, long long fN, long long fC, const float *__restrict__ cd_in,
                    long long dN, long long dC, int R, float qscale, VoxWorkspace ws, int fast_shift) {
   extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the splat grid start launching behind us
   const int map = blockIdx.y;
   int n = map, c = 0;
   if (C != 1) {

@@ -37,6 +37,7 @@ sph_project_kernel(const float *__restrict__ sph, int C, int H, int W, long long
                    long long sW, const float *__restrict__ grid, long long gN, long long gC, long long gH,
                    long long gW, long long gD, int R, float qscale, VoxWorkspace ws) {
   extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the splat grid start launching behind us
   const int map = blockIdx.y;
   const int n = map / C, c = map - n * C;
   const int P = H * W;

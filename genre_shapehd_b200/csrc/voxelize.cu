@@ -65,6 +65,9 @@ vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ov
   __shared__ __align__(16) unsigned s_hi[VOX_TILE];
   const int tile = blockIdx.x, map = blockIdx.y, tid = threadIdx.x;
   const size_t tix = (size_t)map * ntiles + tile;
+  // Programmatic dependent launch: this grid may become resident while the project kernel drains; nothing the
+  // project kernel wrote is read before this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned n = counts[tix];
   const long long start = (long long)tile * VOX_TILE;
   const int nv = (int)min((long long)VOX_TILE, nvox - start);
@@ -151,10 +154,27 @@ vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ov
 template <bool VEC, bool WRITE_CNT>
 static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long long nvox, float *tdf, float *cnt,
                         float alpha, float beta, float bg, cudaStream_t st) {
-  dim3 grid((unsigned)w.ntiles, (unsigned)n_maps);
-  vox_splat_kernel<VEC, WRITE_CNT><<<grid, VOX_SPLAT_THREADS, 0, st>>>(w.buckets, w.ovf, w.counts, w.ovf_count, tdf,
-                                                                       cnt, (long long)P, nvox, w.ntiles, alpha, beta,
-                                                                       bg);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)w.ntiles, (unsigned)n_maps);
+  cfg.blockDim = dim3(VOX_SPLAT_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap this launch with the project kernel's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint2 *buckets = w.buckets, *ovf = w.ovf;
+  const unsigned *counts = w.counts, *ovf_count = w.ovf_count;
+  const long long Pll = (long long)P;
+  const int ntiles = w.ntiles;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vox_splat_kernel<VEC, WRITE_CNT>, buckets, ovf, counts, ovf_count, tdf, cnt,
+                                     Pll, nvox, ntiles, alpha, beta, bg);
+  if (e != cudaSuccess) {
+    set_error("voxelize splat kernel: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
   return check_launch("voxelize splat kernel");
 }
 
