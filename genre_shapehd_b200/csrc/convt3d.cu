@@ -40,6 +40,8 @@ struct ConvTParams {
   float *out;                // blocked [B*2D][cgo][2H][2W][4]
   int cgo;                   // output channel groups
   int base[2];               // input index = j + base[par] - t
+  int srcpar_cgs;            // 0, or: the K range is 8 parity sub-volumes of srcpar_cgs channel groups each (strided
+                             // Conv3d k=4 s=2 p=1 after space-to-depth); sub-volume s = (pz,py,px) uses base 1 - p per dim
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------
@@ -180,14 +182,26 @@ convt3d_s2_kernel(const ConvTParams p) {
   const int y0 = yt * CT_BY;
   const int nchunk = (p.cg0 + p.cg1) / CT_KCG;
 
-  // valid z taps of this slab (a tap plane outside the input contributes nothing: skipped by both sides)
-  int ztaps[T], nz = 0;
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int zi = zj + p.base[pz] - t;
-    if (zi >= 0 && zi < p.D) ztaps[nz++] = t;
-  }
-  const int n_stages_total = nz * nchunk;
+  // Stage enumeration shared by the producer and the MMA issuer: q = tz * nchunk + kc, skipped when the z tap plane
+  // of that K chunk lies outside the input (it contributes nothing).  The per-dimension base offset of a chunk is
+  // uniform (parity class / plain convolution) or a function of the chunk's source sub-volume (strided conv).
+  auto stage_of = [&](int q, int &tz, int &kc, int &bz, int &by, int &bx) -> bool {
+    tz = q / nchunk;
+    kc = q - tz * nchunk;
+    if (p.srcpar_cgs) {
+      const int sv = (kc * CT_KCG) / p.srcpar_cgs;
+      bz = 1 - ((sv >> 2) & 1);
+      by = 1 - ((sv >> 1) & 1);
+      bx = 1 - (sv & 1);
+    } else {
+      bz = p.base[pz];
+      by = p.base[py];
+      bx = p.base[px];
+    }
+    const int zi = zj + bz - tz;
+    return zi >= 0 && zi < p.D;
+  };
+  const int n_q = T * nchunk;
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -210,52 +224,58 @@ convt3d_s2_kernel(const ConvTParams p) {
 
   if (warp < 4) {
     // ===================== producers: halo (cp.async, zero-fill) + weights (one bulk copy per stage) ==========
-    // this thread's halo positions are the same for every stage: precompute (offset in cg plane, y, x, validity)
-    int hoff[Cfg::POS_PER_THREAD], gy[Cfg::POS_PER_THREAD], gx[Cfg::POS_PER_THREAD];
+    // this thread's halo positions are the same for every stage: precompute (offset in the cg plane, halo row/col)
+    int hoff[Cfg::POS_PER_THREAD], hy[Cfg::POS_PER_THREAD], hx[Cfg::POS_PER_THREAD];
 #pragma unroll
     for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
       const int idx = tid + i * CT_PRODUCERS;
-      const int hy = idx / Cfg::PX, hx = idx - hy * Cfg::PX;
+      hy[i] = idx / Cfg::PX;
+      hx[i] = idx - hy[i] * Cfg::PX;
       hoff[i] = idx < Cfg::POS ? idx * 16 : -1;
-      gy[i] = y0 + p.base[py] - (T - 1) + hy;  // halo row hy holds input row y0 + base - (T-1) + hy
-      gx[i] = p.base[px] - (T - 1) + hx;
     }
     constexpr int LAG = Cfg::STAGES - 1 < 2 ? 1 : 2;  // cp.async groups in flight before a stage is published
-    for (int it = 0; it < n_stages_total + LAG; ++it) {
-      if (it < n_stages_total) {
-        const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
-        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-        const int zt = ztaps[it / nchunk], kc = it % nchunk;
-        uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
-        if (tid == 0) {
-          const float *wsrc = p.wpack + ((((size_t)par * T + zt) * nchunk + kc) * (size_t)(Cfg::B_BYTES / 4));
-          mbar_arrive_expect_tx(&full[s], Cfg::B_BYTES);
-          bulk_g2s(sa + Cfg::A_BYTES, wsrc, Cfg::B_BYTES, &full[s]);
-        }
-        const int zi = zj + p.base[pz] - zt;
-#pragma unroll
-        for (int c = 0; c < CT_KCG; ++c) {
-          int cg = kc * CT_KCG + c;
-          const float *src = p.src0;
-          int ncg = p.cg0;
-          if (cg >= p.cg0) { cg -= p.cg0; src = p.src1; ncg = p.cg1; }
-          const float *plane = src + ((((size_t)b * p.D + zi) * ncg + cg) * p.H) * (size_t)p.W * 4;
-#pragma unroll
-          for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
-            if (hoff[i] < 0) continue;
-            const bool ok = (gy[i] >= 0) & (gy[i] < p.H) & (gx[i] >= 0) & (gx[i] < p.W);
-            const float *g = ok ? plane + ((size_t)gy[i] * p.W + gx[i]) * 4 : plane;
-            cp_async16_zfill(sa + c * Cfg::A_CG_BYTES + hoff[i], g, ok);
-          }
-        }
-      }
+    int it = 0;                                        // stages issued so far
+    auto publish = [&]() {  // after committing group `it`: group it - LAG has landed -> hand it to the async proxy
       cp_async_commit();
-      if (it >= LAG) {  // the group of stage (it - LAG) has landed: publish it to the tensor-core (async) proxy
+      if (it >= LAG) {
         cp_async_wait<LAG>();
         fence_proxy_async_smem();
         mbar_arrive(&full[(it - LAG) % Cfg::STAGES]);
       }
+      ++it;
+    };
+    for (int q = 0; q < n_q; ++q) {
+      int tz, kc, bz, by, bx;
+      if (!stage_of(q, tz, kc, bz, by, bx)) continue;
+      const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
+      if (tid == 0) {
+        const float *wsrc = p.wpack + ((((size_t)par * T + tz) * nchunk + kc) * (size_t)(Cfg::B_BYTES / 4));
+        mbar_arrive_expect_tx(&full[s], Cfg::B_BYTES);
+        bulk_g2s(sa + Cfg::A_BYTES, wsrc, Cfg::B_BYTES, &full[s]);
+      }
+      const int zi = zj + bz - tz;
+      const int gy0 = y0 + by - (T - 1), gx0 = bx - (T - 1);  // halo row hy holds input row gy0 + hy
+#pragma unroll
+      for (int c = 0; c < CT_KCG; ++c) {
+        int cg = kc * CT_KCG + c;
+        const float *src = p.src0;
+        int ncg = p.cg0;
+        if (cg >= p.cg0) { cg -= p.cg0; src = p.src1; ncg = p.cg1; }
+        const float *plane = src + ((((size_t)b * p.D + zi) * ncg + cg) * p.H) * (size_t)p.W * 4;
+#pragma unroll
+        for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
+          if (hoff[i] < 0) continue;
+          const int gy = gy0 + hy[i], gx = gx0 + hx[i];
+          const bool ok = (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
+          const float *g = ok ? plane + ((size_t)gy * p.W + gx) * 4 : plane;
+          cp_async16_zfill(sa + c * Cfg::A_CG_BYTES + hoff[i], g, ok);
+        }
+      }
+      publish();
     }
+    for (int e = 0; e < LAG; ++e) publish();  // drain: empty groups push the last real ones through
 
     // ===================== epilogue: TMEM -> registers -> act(acc*scale+shift) -> blocked global store =========
     mbar_wait(accum_full, 0);
@@ -294,8 +314,12 @@ convt3d_s2_kernel(const ConvTParams p) {
     // ===================== MMA issuer (one thread) =============================================================
     constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, NPAD) : umma_idesc_tf32(128, NPAD);
     bool first = true;
-    for (int it = 0; it < n_stages_total; ++it) {
+    int it = 0;
+    for (int q = 0; q < n_q; ++q) {
+      int tz, kc, bz, by, bx;
+      if (!stage_of(q, tz, kc, bz, by, bx)) continue;
       const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
+      ++it;
       mbar_wait(&full[s], use & 1);
       tc_fence_after();
       const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
@@ -317,9 +341,6 @@ convt3d_s2_kernel(const ConvTParams p) {
       }
       first = false;
       umma_commit(&empty[s]);  // frees the slot when the MMAs that read it are done (implies fence::before_thread_sync)
-    }
-    if (n_stages_total == 0) {
-      // cannot happen for a valid layer (every output has at least one z tap); keep the protocol sound anyway
     }
     umma_commit(accum_full);
   }
@@ -387,6 +408,7 @@ extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const v
   p.src0 = src0; p.src1 = src1; p.cg0 = cg0; p.cg1 = cg1;
   p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
   p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  p.srcpar_cgs = 0;
   const int pad = ksize / 2 - 1;
   for (int par = 0; par < 2; ++par) {
     const int k0 = (par + pad) % 2;
@@ -434,6 +456,7 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   p.src0 = src0; p.src1 = src1; p.cg0 = cg0; p.cg1 = cg1;
   p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
   p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  p.srcpar_cgs = 0;
   p.base[0] = p.base[1] = base;
   cudaStream_t st = as_stream(stream);
 #define GB_CV(TT, MM) return launch_convt<TT, 32, MM, false>(p, st)
@@ -445,4 +468,46 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   if (taps == 3 && W == 16) GB_CV(3, 2);
 #undef GB_CV
   return fail_arg(GENRE_B200_EINVAL, "conv3d_taps: no kernel instance");
+}
+
+// Conv3d(kernel 4, stride 2, padding 1) forward (VoxelDiscriminator networks/networks.py:247-250 conv3d_half, Unet_3D
+// enc2..enc5 :152-155) on the same kernel: the input arrives as its 8 parity sub-volumes in ONE channel-blocked tensor
+//   src [B*D'][8*cgs][H'][W'][16 B]   (D' = D/2 ...; channel group index = s*cgs + c, s = (pz*2+py)*2+px)
+// and sub-volume s is a K range with 2 taps per dimension: in[2(o+delta)+p] with delta = (1-p) - t, k = 3 - 2t - p.
+//   wpack [2 z-tap][8*cgs/2 chunk][4 taps][2][npad/8][8][g];  out [B*D'][cgo][H'][W'][4] fp32
+// Supported: W' in {16, 32}, H' % 16 == 0, cgs even, npad in {32, 64, 96, 128}.
+extern "C" int genre_b200_conv3d_k4s2_forward(const void *src_, int cgs, int64_t B, int64_t D, int64_t H, int64_t W,
+                                              const void *wpack_, int npad, int f16, const float *scale,
+                                              const float *shift, float slope, float *out, int cgo, void *stream) {
+  const float *src = (const float *)src_, *wpack = (const float *)wpack_;
+  g_conv_f16 = f16 != 0;
+  GB_REQUIRE(src && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_k4s2: null pointer");
+  GB_REQUIRE(npad == 32 || npad == 64 || npad == 96 || npad == 128, GENRE_B200_EINVAL, "conv3d_k4s2: npad %d", npad);
+  GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "conv3d_k4s2: output width %lld unsupported (16 or 32)", (long long)W);
+  GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_k4s2: bad extent");
+  GB_REQUIRE(cgs > 0 && cgs % CT_KCG == 0, GENRE_B200_EINVAL, "conv3d_k4s2: channel groups per sub-volume must be even");
+  GB_REQUIRE(cgo > 0 && 4 * cgo <= npad, GENRE_B200_EINVAL, "conv3d_k4s2: too many output channels");
+  GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "conv3d_k4s2: grid too large");
+  GB_REQUIRE(aligned16(src) && aligned16(wpack) && aligned16(out), GENRE_B200_EALIGN, "conv3d_k4s2: alignment");
+  ConvTParams p;
+  p.src0 = src; p.src1 = nullptr; p.cg0 = 8 * cgs; p.cg1 = 0;
+  p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
+  p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  p.srcpar_cgs = cgs;
+  p.base[0] = p.base[1] = 0;
+  cudaStream_t st = as_stream(stream);
+#define GB_CS(NN, MM) return launch_convt<2, NN, MM, false>(p, st)
+  if (W == 32) {
+    if (npad == 32) GB_CS(32, 4);
+    if (npad == 64) GB_CS(64, 4);
+    if (npad == 96) GB_CS(96, 4);
+    if (npad == 128) GB_CS(128, 4);
+  } else {
+    if (npad == 32) GB_CS(32, 2);
+    if (npad == 64) GB_CS(64, 2);
+    if (npad == 96) GB_CS(96, 2);
+    if (npad == 128) GB_CS(128, 2);
+  }
+#undef GB_CS
+  return fail_arg(GENRE_B200_EINVAL, "conv3d_k4s2: no kernel instance");
 }

@@ -19,11 +19,26 @@ import torch
 from . import _lib
 
 ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
+# Dispatch policy.  Every kernel is correct on every layer it supports (tests force all of them on), but around a
+# kernel sit two layout conversions (NCDHW <-> channel-blocked); measured end to end on a B200 (profiles/
+# r01_conv_summary.md) the custom path wins where cuDNN is far off its own pace and is break-even or slower on the
+# "ordinary" k=4 layers, so by default only the winning cases are routed here:
+#   convt_k8   ConvTranspose3d k=8 s=2 (Unet_3D.dec5: 7.2 -> 3.5 ms)                                       ON
+#   conv_k8s2  Conv3d k=8 s=2 on few input channels (Unet_3D.enc1: 16.6 -> 2.2 ms)                         ON
+#   convt_c1   ConvTranspose3d k=4 -> 1 channel when the inputs are already blocked (Unet_3D.dec6: 2.1 -> 1.4) ON
+#   convt_k4   ConvTranspose3d k=4 s=2 (dec4, VoxelDecoder/Generator stages: kernel faster, conversions eat it)  off
+#   conv_k4s2  Conv3d k=4 s=2 (discriminator, enc2/enc3: slower end to end)                                  off
+#   convt_c1_convert   the 1-channel layer when its input must first be converted (VoxelDecoder/Generator)   off
+# GENRE_B200_CONV_POLICY="all" (or a comma list) overrides.
+_default_policy = {"convt_k8", "conv_k8s2", "convt_c1"}
+_all_policy = _default_policy | {"convt_k4", "conv_k4s2", "convt_c1_convert"}
+_env = os.environ.get("GENRE_B200_CONV_POLICY", "")
+POLICY = set(_all_policy) if _env == "all" else (set(x for x in _env.split(",") if x) or set(_default_policy))
+K4S2_MIN_CIN = 8
 # Operand type of the tensor-core kernels: "f16" (default) = fp16 operands, fp32 accumulation: the same 10-bit
 # mantissa as TF32 with half the operand bytes (the kernels are bound by shared-memory operand bandwidth, so ~2x
 # faster); "tf32" = fp32 storage read as TF32.  Both accumulate in fp32 and produce fp32 activations.
 PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "f16")
-_wcache = {}
 
 
 def _f16():
@@ -87,20 +102,29 @@ def pack_convt_weights(weight, npad, group=4):
     return out.half() if g == 8 else out
 
 
-def _packed(module, npad):
+def _cached_pack(module, key, make):
+    """Packed weights live ON the module (they die with it; a global cache keyed by id() could hand a recycled id the
+    weights of a dead layer) and are rebuilt when the parameter is updated in place (optimizer step, load_state_dict)."""
     w = module.weight
-    key = (id(module), npad, _group())
-    ver = (w._version, w.data_ptr(), w.device)
-    hit = _wcache.get(key)
+    cache = module.__dict__.setdefault("_gb_packed", {})
+    ver = (w._version, w.data_ptr(), str(w.device))
+    hit = cache.get(key)
     if hit is None or hit[0] != ver:
-        hit = (ver, pack_convt_weights(w.detach(), npad, _group()))
-        _wcache[key] = hit
+        hit = (ver, make(w.detach()))
+        cache[key] = hit
     return hit[1]
+
+
+def _packed(module, npad):
+    g = _group()
+    return _cached_pack(module, ("convt", npad, g), lambda w: pack_convt_weights(w, npad, g))
 
 
 def _convt_supported(shape_bcdhw, module):
     b, c, d, h, w = shape_bcdhw
     k = module.kernel_size[0]
+    if ("convt_k8" if k == 8 else "convt_k4") not in POLICY:
+        return False
     return (ENABLED and tuple(module.kernel_size) == (k, k, k) and k in (4, 8) and tuple(module.stride) == (2, 2, 2)
             and tuple(module.padding) == (k // 2 - 1,) * 3 and tuple(module.output_padding) == (0, 0, 0)
             and tuple(module.dilation) == (1, 1, 1) and module.groups == 1 and w in (16, 32) and h % 16 == 0
@@ -176,29 +200,62 @@ def pack_conv_k8s2_weights(weight, npad, group=4):
 
 
 def _packed_conv(module, npad):
-    w = module.weight
-    key = (id(module), npad, "k8s2", _group())
-    ver = (w._version, w.data_ptr(), w.device)
-    hit = _wcache.get(key)
-    if hit is None or hit[0] != ver:
-        hit = (ver, pack_conv_k8s2_weights(w.detach(), npad, _group()))
-        _wcache[key] = hit
-    return hit[1]
+    g = _group()
+    return _cached_pack(module, ("k8s2", npad, g), lambda w: pack_conv_k8s2_weights(w, npad, g))
 
 
 def _conv_k8s2_supported(x, m):
-    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and tuple(m.kernel_size) == (8, 8, 8)
+    return ("conv_k8s2" in POLICY and ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and tuple(m.kernel_size) == (8, 8, 8)
             and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (3, 3, 3) and tuple(m.dilation) == (1, 1, 1)
             and m.groups == 1 and m.out_channels <= 32 and x.shape[1] % 2 == 0 and x.shape[1] <= 8
             and all(v % 2 == 0 for v in x.shape[2:]) and x.shape[4] // 2 in (16, 32, 64) and (x.shape[3] // 2) % 16 == 0
             and m.padding_mode == "zeros")
 
 
-def conv3d(x, m, bn=None, slope=None):
-    """Conv3d(k=8, s=2, p=3) on few input channels (Unet_3D.enc1) [+ folded eval BatchNorm3d + LeakyReLU]."""
-    if not (_conv_k8s2_supported(x, m) and _no_autograd(x, m.weight, m.bias)):
-        return None
-    cout, npad = m.out_channels, 32
+def space_to_depth_sources(x, cpad, group, dtype):
+    """NCDHW [B,C,D,H,W] (even extents) -> [B*D/2, 8*cpad/group, H/2, W/2, group]: the 8 parity sub-volumes one after the
+    other along the channel-group axis (sub-volume s = (pz*2+py)*2+px holds in[2z'+pz, 2y'+py, 2x'+px]), each zero-padded
+    from C to cpad channels."""
+    b, c, d, h, w = x.shape
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if cpad != c:
+        x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 0, 0, cpad - c))
+    t = x.reshape(b, cpad // group, group, d // 2, 2, h // 2, 2, w // 2, 2)      # b cg e z' pz y' py x' px
+    t = t.permute(0, 3, 4, 6, 8, 1, 5, 7, 2)                                      # b z' pz py px cg y' x' e
+    return t.reshape(b * (d // 2), 8 * (cpad // group), h // 2, w // 2, group).contiguous()
+
+
+def pack_conv_k4s2_weights(weight, cpad, npad, group):
+    """Conv3d weight [Cout, Cin, 4, 4, 4] (stride 2, padding 1) -> [2 z-tap][8*cpad/(2g) chunk][4 taps][2][npad/8][8][g]:
+    sub-volume s = (pz,py,px) and tap t use kernel index k = 3 - 2t - p per dimension."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    g = group
+    weq = weight.new_zeros((8, cpad, npad, 2, 2, 2))                              # (s, ci, n, tz, ty, tx)
+    for pz in (0, 1):
+        for py in (0, 1):
+            for px in (0, 1):
+                sidx = (pz * 2 + py) * 2 + px
+                for tz in (0, 1):
+                    for ty in (0, 1):
+                        for tx in (0, 1):
+                            weq[sidx, :cin, :cout, tz, ty, tx] = weight[:, :, 3 - 2 * tz - pz, 3 - 2 * ty - py, 3 - 2 * tx - px].t()
+    sub = weq.reshape(8 * cpad // (2 * g), 2, g, npad // 8, 8, 2, 2, 2)           # (kc, kk, e, ng, r, tz, ty, tx)
+    out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                        # (tz, kc, ty, tx, kk, ng, r, e)
+    return out.half() if g == 8 else out
+
+
+def _conv_k4s2_supported(x, m):
+    return ("conv_k4s2" in POLICY and ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and tuple(m.kernel_size) == (4, 4, 4)
+            and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1) and tuple(m.dilation) == (1, 1, 1)
+            and m.groups == 1 and m.out_channels <= 128 and x.shape[1] >= K4S2_MIN_CIN and m.padding_mode == "zeros"
+            and x.shape[1] % (2 * _group()) == 0
+            and all(v % 2 == 0 for v in x.shape[2:]) and x.shape[4] // 2 in (16, 32) and (x.shape[3] // 2) % 16 == 0)
+
+
+def _affine(m, bn, npad, dev):
+    """(scale, shift) [npad] of the epilogue: bias, and eval-mode BatchNorm folded in; None if bn needs batch statistics"""
+    cout = m.out_channels
     scale = shift = None
     if bn is not None:
         if bn.training or not bn.track_running_stats:
@@ -207,11 +264,48 @@ def conv3d(x, m, bn=None, slope=None):
         scale = inv * (bn.weight if bn.weight is not None else 1.0)
         bias = m.bias.detach() if m.bias is not None else torch.zeros_like(bn.running_mean)
         shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
-    dev = x.device
     sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
     if shift is None:
         shift = m.bias.detach() if m.bias is not None else torch.zeros(cout, device=dev)
-    sh = torch.nn.functional.pad(shift.float(), (0, npad - cout))
+    return sc, torch.nn.functional.pad(shift.float(), (0, npad - cout))
+
+
+def _conv_k4s2(x, m, bn, slope):
+    cout = m.out_channels
+    npad = 32 * ((cout + 31) // 32)
+    aff = _affine(m, bn, npad, x.device)
+    if aff is None:
+        return None
+    g = _group()
+    cin = x.shape[1]
+    cpad = (cin + 2 * g - 1) // (2 * g) * (2 * g)      # a K chunk (2 channel groups) must not straddle sub-volumes
+    wpack = _cached_pack(m, ("k4s2", cpad, npad, g), lambda w: pack_conv_k4s2_weights(w, cpad, npad, g))
+    xb = space_to_depth_sources(x, cpad, g, torch.float16 if _f16() else None)
+    b = x.shape[0]
+    bd, _, h, wd, _ = xb.shape
+    cgo = (cout + 3) // 4
+    out = torch.empty((bd, cgo, h, wd, 4), device=x.device, dtype=torch.float32)
+    _lib.call("genre_b200_conv3d_k4s2_forward", xb.data_ptr(), cpad // g, b, bd // b, h, wd, wpack.data_ptr(), npad,
+              1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
+              out.data_ptr(), cgo, _lib.stream_ptr(x))
+    return from_blocked(out, b, cout)
+
+
+def conv3d(x, m, bn=None, slope=None):
+    """Conv3d on the tcgen05 kernel [+ folded eval BatchNorm3d + LeakyReLU]: k=8,s=2,p=3 on few input channels
+    (Unet_3D.enc1) via space-to-depth, or k=4,s=2,p=1 (discriminator, Unet_3D.enc2/enc3) via parity sub-volumes."""
+    if not x.is_cuda or not _no_autograd(x, m.weight, m.bias):
+        return None
+    if _conv_k4s2_supported(x, m):
+        return _conv_k4s2(x, m, bn, slope)
+    if not _conv_k8s2_supported(x, m):
+        return None
+    cout, npad = m.out_channels, 32
+    aff = _affine(m, bn, npad, x.device)
+    if aff is None:
+        return None
+    sc, sh = aff
+    dev = x.device
     xb = space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x)
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
@@ -223,7 +317,15 @@ def conv3d(x, m, bn=None, slope=None):
     return from_blocked(out, b, cout)
 
 
-def _convt_c1_supported(cin, shape_dhw, m):
+def _has_blocked(x):
+    return getattr(x, "_gb_blocked", None) is not None
+
+
+def _convt_c1_supported(cin, shape_dhw, m, inputs=()):
+    if "convt_c1" not in POLICY:
+        return False
+    if "convt_c1_convert" not in POLICY and not all(_has_blocked(t) for t in inputs):
+        return False
     return (ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1)
             and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1
             and m.out_channels == 1 and cin % 4 == 0 and cin <= 192 and shape_dhw[2] % 4 == 0)
@@ -243,7 +345,7 @@ def convt_c1(src0, src1, batch, m):
 
 
 def conv_transpose3d(x, m):
-    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_c1_supported(x.shape[1], x.shape[2:], m)
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_c1_supported(x.shape[1], x.shape[2:], m, (x,))
             and _no_autograd(x, m.weight, m.bias)):
         return convt_c1(_blocked_f32(x), None, x.shape[0], m)
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_supported(x.shape, m)
@@ -258,7 +360,7 @@ def deconv_skip(x, skip, conv, bn=None, slope=None):
     concatenation walked as two K ranges instead of being materialised.  None if not covered."""
     if (bn is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
             and x.shape[1] % 4 == 0 and skip.shape[1] % 4 == 0
-            and _convt_c1_supported(x.shape[1] + skip.shape[1], x.shape[2:], conv)
+            and _convt_c1_supported(x.shape[1] + skip.shape[1], x.shape[2:], conv, (x, skip))
             and _no_autograd(x, skip, conv.weight, conv.bias)):
         return convt_c1(_blocked_f32(x), _blocked_f32(skip), x.shape[0], conv)
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]

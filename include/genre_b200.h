@@ -198,6 +198,17 @@ int genre_b200_conv3d_taps_forward(const void *src0, int cg0, const void *src1, 
                                    const float *scale, const float *shift, float slope,
                                    float *out, int cgo, void *stream);
 
+/* Conv3d(kernel 4, stride 2, padding 1) forward on the same tcgen05 kernel.  Replaces the cuDNN call behind conv3d_half
+ * (VoxelDiscriminator, networks/networks.py:247-250) and Unet_3D.enc2..enc5 (:152-155).  The input arrives as its 8 parity
+ * sub-volumes in one channel-blocked tensor src [B*D'][8*cgs][H'][W'][16 B] (D' = D/2 ...; group index = s*cgs + c,
+ * s = (pz*2+py)*2+px); sub-volume s is a K range with 2 taps per dimension (kernel index 3 - 2t - p).
+ *   wpack [2][8*cgs/2][4][2][npad/8][8][g];  out [B*D'][cgo][H'][W'][4];  W' in {16,32}, H' % 16 == 0, cgs even,
+ *   npad in {32,64,96,128}. */
+int genre_b200_conv3d_k4s2_forward(const void *src, int cgs, int64_t B, int64_t D, int64_t H, int64_t W,
+                                   const void *wpack, int npad, int f16,
+                                   const float *scale, const float *shift, float slope,
+                                   float *out, int cgo, void *stream);
+
 /* ConvTranspose3d(Cin -> 1, kernel 4, stride 2, padding 1) forward on channel-blocked fp32 inputs (FP32 pipe: with one
  * output channel there is no GEMM for the tensor cores).  Replaces the cuDNN call behind the last layer of each decoder:
  * Unet_3D.dec6 (networks/networks.py:167-168, two sources = the skip concatenation), VoxelDecoder main.17 (:57),

@@ -53,6 +53,31 @@ with torch.no_grad():
         t_cudnn_fp32 = timeit(lambda: F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=m.padding))
         out[name] = {"gflop": flop / 1e9, "kernel_ms": t_kernel, "kernel_tflops": flop / t_kernel / 1e9,
                      "with_layout_conversion_ms": t_total, "cudnn_tf32_ms": t_cudnn_tf32, "cudnn_fp32_ms": t_cudnn_fp32}
+    # discriminator: strided Conv3d layers (k4 s2) and the whole forward
+    for name, (cin, cout, sp) in {"disc2_conv_64_64": (64, 64, 64), "disc3_conv_64_128": (64, 128, 32)}.items():
+        m = nets.Conv3d(cin, cout, 4, 2, 1, bias=False).to(dev)
+        x = torch.randn(B, cin, sp, sp, sp, device=dev)
+        flop = 2.0 * B * (sp // 2) ** 3 * cout * cin * 64
+        torch.backends.cudnn.allow_tf32 = True
+        t_custom = timeit(lambda: ops_conv.conv3d(x, m))
+        t_cudnn = timeit(lambda: F.conv3d(x, m.weight, None, stride=2, padding=1))
+        out[name] = {"gflop": flop / 1e9, "custom_with_conversions_ms": t_custom, "cudnn_tf32_ms": t_cudnn}
+    dnet = nets.VoxelDiscriminator().to(dev).eval()
+    xd = torch.rand(B, 1, 128, 128, 128, device=dev)
+    torch.backends.cudnn.allow_tf32 = True
+    ops_conv.ENABLED = True
+    out["discriminator_custom_ms"] = timeit(lambda: dnet(xd), reps=5, warm=2)
+    ops_conv.ENABLED = False
+    out["discriminator_cudnn_tf32_ms"] = timeit(lambda: dnet(xd), reps=5, warm=2)
+    ops_conv.ENABLED = True
+    for nm, cls in (("voxeldecoder", nets.VoxelDecoder), ("generator", nets.VoxelGenerator)):
+        net_ = cls().to(dev).eval()
+        z = torch.randn(B, 200, device=dev) if nm == "voxeldecoder" else torch.randn(B, 200, 1, 1, 1, device=dev)
+        ops_conv.ENABLED = True
+        out[nm + "_custom_ms"] = timeit(lambda: net_(z), reps=5, warm=2)
+        ops_conv.ENABLED = False
+        out[nm + "_cudnn_tf32_ms"] = timeit(lambda: net_(z), reps=5, warm=2)
+        ops_conv.ENABLED = True
     # whole refiner, eval mode
     net = nets.Unet_3D().to(dev).eval()
     x = torch.rand(B, 2, 128, 128, 128, device=dev)

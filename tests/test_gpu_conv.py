@@ -14,10 +14,11 @@ DEV = "cuda:0"
 def _precision(request):
     """every test runs with both operand types of the tensor-core kernels"""
     torch.backends.cudnn.allow_tf32 = True   # the custom kernels decline when reduced-mantissa convolutions are disallowed
-    old = ops_conv.PRECISION
+    old, oldp = ops_conv.PRECISION, set(ops_conv.POLICY)
     ops_conv.PRECISION = request.param
+    ops_conv.POLICY = set(ops_conv._all_policy)   # exercise every kernel, not only the ones routed by default
     yield
-    ops_conv.PRECISION = old
+    ops_conv.PRECISION, ops_conv.POLICY = old, oldp
     torch.backends.cudnn.allow_tf32 = True
 
 
@@ -142,3 +143,32 @@ def test_dec6_two_source_path_vs_torch():
         ref = blk.net(torch.cat((x, s), 1))
         torch.backends.cudnn.allow_tf32 = True
     assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,b,d,h,w", [(16, 24, 1, 4, 32, 32), (64, 64, 1, 6, 64, 64), (20, 40, 2, 8, 64, 64),
+                                              (40, 80, 1, 4, 32, 32), (64, 128, 1, 4, 32, 64)])
+def test_conv3d_k4s2_parity_subvolumes_vs_torch(cin, cout, b, d, h, w, monkeypatch):
+    monkeypatch.setattr(ops_conv, "K4S2_MIN_CIN", 8)   # exercise the kernel on small layers too
+    if cin % (2 * ops_conv._group()) != 0:
+        pytest.skip("channel count not a multiple of the K chunk for this operand type")
+    torch.manual_seed(cin + cout + w)
+    m = nets.Conv3d(cin, cout, 4, 2, 1, bias=(cout % 3 != 0)).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV)
+    with torch.no_grad():
+        y = ops_conv.conv3d(x, m)
+        assert y is not None
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=1)
+        torch.backends.cudnn.allow_tf32 = True
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+def test_default_policy_routes_only_the_winning_layers():
+    ops_conv.POLICY = set(ops_conv._default_policy)
+    with torch.no_grad():
+        assert ops_conv.conv_transpose3d(torch.randn(1, 80, 2, 32, 32, device=DEV), nets.ConvTranspose3d(80, 20, 8, 2, 3).to(DEV)) is not None
+        assert ops_conv.conv3d(torch.rand(1, 2, 4, 64, 64, device=DEV), nets.Conv3d(2, 20, 8, 2, 3).to(DEV)) is not None
+        assert ops_conv.conv_transpose3d(torch.randn(1, 64, 2, 32, 32, device=DEV), nets.ConvTranspose3d(64, 32, 4, 2, 1).to(DEV)) is None
+        assert ops_conv.conv3d(torch.randn(1, 64, 4, 64, 64, device=DEV), nets.Conv3d(64, 64, 4, 2, 1).to(DEV)) is None
+        assert ops_conv.conv_transpose3d(torch.randn(1, 32, 2, 16, 16, device=DEV), nets.ConvTranspose3d(32, 1, 4, 2, 1).to(DEV)) is None
