@@ -139,6 +139,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 4-column reads (the two x-parity classes of one channel group) behind one wait
+__device__ __forceinline__ void tmem_ld4x2(uint32_t taddr0, uint32_t taddr1, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%8];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%9];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr0), "r"(taddr1)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------
 // T: taps per dimension of a parity class (K/2: 2 for k=4, 4 for k=8); NPAD: padded Cout (32 or 64); MT = W/8.
 template <int T, int NPAD, int MT>
@@ -159,12 +173,19 @@ struct ConvTCfg {
   static_assert(MT * NPAD <= 512, "accumulators exceed TMEM");
 };
 
-// PAR = true : 8 parity classes (blockIdx.y), output at 2*j + parity (ConvTranspose3d stride 2)
-// PAR = false: one class, output at j (stride-1 tap convolution; strided Conv3d arrives here after space-to-depth)
-template <int T, int NPAD, int MT, bool PAR, bool F16>
+// MODE 0: 8 parity classes (blockIdx.y), output at 2*j + parity (ConvTranspose3d stride 2); TZ = T = K/2 taps
+// MODE 1: one class, output at j (stride-1 tap convolution; strided Conv3d arrives here after space-to-depth)
+// MODE 2: ConvTranspose3d stride 2 with the four (y,x) parity classes MERGED along N (blockIdx.y = z parity): the
+//         classes read the same halo at offsets that overlap in all but one tap per dimension, so one MMA over the
+//         union of T = K/2 + 1 taps with N = 4 * Cout columns (n = (py*2+px)*Cout + co, zero weights where a class
+//         does not use a tap) replaces four N = Cout MMAs.  An M128 MMA costs about the same 64+ cycles for any
+//         N <= 128 (the A operand streams from shared memory at a fixed rate), so this is ~2.5x fewer tensor cycles.
+//         TZ = K/2 z taps of the CTA's z parity.
+template <int TZ, int T, int NPAD, int MT, int MODE, bool F16>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 convt3d_s2_kernel(const ConvTParams p) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
+  constexpr bool PAR = MODE == 0, MERGE = MODE == 2;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *stages = smem;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -174,7 +195,7 @@ convt3d_s2_kernel(const ConvTParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int par = blockIdx.y;  // parity class: bit 2 = z, bit 1 = y, bit 0 = x
-  const int pz = (par >> 2) & 1, py = (par >> 1) & 1, px = par & 1;
+  const int pz = MERGE ? par : (par >> 2) & 1, py = (par >> 1) & 1, px = par & 1;
   const int ytiles = p.H / CT_BY;
   const int yt = blockIdx.x % ytiles;
   const int zj = (blockIdx.x / ytiles) % p.D;
@@ -195,13 +216,13 @@ convt3d_s2_kernel(const ConvTParams p) {
       bx = 1 - (sv & 1);
     } else {
       bz = p.base[pz];
-      by = p.base[py];
-      bx = p.base[px];
+      by = MERGE ? T / 2 : p.base[py];
+      bx = MERGE ? T / 2 : p.base[px];
     }
     const int zi = zj + bz - tz;
     return zi >= 0 && zi < p.D;
   };
-  const int n_q = T * nchunk;
+  const int n_q = TZ * nchunk;
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -251,7 +272,7 @@ convt3d_s2_kernel(const ConvTParams p) {
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
       uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
       if (tid == 0) {
-        const float *wsrc = p.wpack + ((((size_t)par * T + tz) * nchunk + kc) * (size_t)(Cfg::B_BYTES / 4));
+        const float *wsrc = p.wpack + ((((size_t)par * TZ + tz) * nchunk + kc) * (size_t)(Cfg::B_BYTES / 4));
         mbar_arrive_expect_tx(&full[s], Cfg::B_BYTES);
         bulk_g2s(sa + Cfg::A_BYTES, wsrc, Cfg::B_BYTES, &full[s]);
       }
@@ -282,8 +303,43 @@ convt3d_s2_kernel(const ConvTParams p) {
     tc_fence_after();
     const int m = warp * 32 + lane;  // accumulator row = TMEM lane
     const int yy = m >> 3, xx = m & 7;
-    const int Ho = PAR ? 2 * p.H : p.H, Wo = PAR ? 2 * p.W : p.W, Do = PAR ? 2 * p.D : p.D;
-    const int oz = PAR ? 2 * zj + pz : zj, oy = PAR ? 2 * (y0 + yy) + py : y0 + yy;
+    constexpr bool UP = PAR || MERGE;
+    const int Ho = UP ? 2 * p.H : p.H, Wo = UP ? 2 * p.W : p.W, Do = UP ? 2 * p.D : p.D;
+    const int oz = UP ? 2 * zj + pz : zj, oy = PAR ? 2 * (y0 + yy) + py : y0 + yy;
+    if constexpr (MERGE) {
+      constexpr int CP = NPAD / 4;  // output channels per (y,x) parity class
+      static_assert(CP % 4 == 0, "merged classes must be whole channel groups");
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int oxb = 2 * (8 * mt + xx);
+#pragma unroll
+        for (int qy = 0; qy < 2; ++qy) {
+          const int oyy = 2 * (y0 + yy) + qy;
+#pragma unroll
+          for (int cgo = 0; cgo < CP / 4; ++cgo) {
+            if (cgo >= p.cgo) continue;  // uniform across the CTA
+            float v[8];
+            tmem_ld4x2(trow + (uint32_t)(mt * NPAD + (qy * 2) * CP + cgo * 4),
+                       trow + (uint32_t)(mt * NPAD + (qy * 2 + 1) * CP + cgo * 4), v);
+            float4 o[2];
+#pragma unroll
+            for (int qx = 0; qx < 2; ++qx) {
+              float *po = &o[qx].x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int n = cgo * 4 + e;
+                const float t = fmaf(v[qx * 4 + e], __ldg(p.scale + n), __ldg(p.shift + n));
+                po[e] = t > 0.0f ? t : t * p.slope;
+              }
+            }
+            float *dst = p.out + (((((size_t)b * Do + oz) * p.cgo + cgo) * Ho + oyy) * (size_t)Wo + oxb) * 4;
+            *reinterpret_cast<float4 *>(dst) = o[0];
+            *reinterpret_cast<float4 *>(dst + 4) = o[1];
+          }
+        }
+      }
+    } else {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int ox = PAR ? 2 * (8 * mt + xx) + px : 8 * mt + xx;
@@ -308,6 +364,7 @@ convt3d_s2_kernel(const ConvTParams p) {
           }
         }
       }
+    }
     }
     tc_fence_before();
   } else if (lane == 0) {
@@ -351,10 +408,10 @@ convt3d_s2_kernel(const ConvTParams p) {
   }
 }
 
-template <int T, int NPAD, int MT, bool PAR, bool F16>
+template <int TZ, int T, int NPAD, int MT, int MODE, bool F16>
 static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
-  auto kern = convt3d_s2_kernel<T, NPAD, MT, PAR, F16>;
+  auto kern = convt3d_s2_kernel<TZ, T, NPAD, MT, MODE, F16>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -366,7 +423,7 @@ static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
     }
     configured[dev & 63] = true;
   }
-  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY)), PAR ? 8 : 1);
+  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY)), MODE == 0 ? 8 : MODE == 2 ? 2 : 1);
   kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(p);
   return check_launch("convt3d_s2 kernel");
 }
@@ -374,7 +431,12 @@ static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
 static thread_local bool g_conv_f16 = false;  // operand type of the next launch (set by the C ABI entry points)
 template <int T, int NPAD, int MT, bool PAR>
 static int launch_convt(const ConvTParams &p, cudaStream_t st) {
-  return g_conv_f16 ? launch_convt_impl<T, NPAD, MT, PAR, true>(p, st) : launch_convt_impl<T, NPAD, MT, PAR, false>(p, st);
+  return g_conv_f16 ? launch_convt_impl<T, T, NPAD, MT, PAR ? 0 : 1, true>(p, st)
+                    : launch_convt_impl<T, T, NPAD, MT, PAR ? 0 : 1, false>(p, st);
+}
+template <int TZ, int T, int NPAD, int MT>
+static int launch_convt_merged(const ConvTParams &p, cudaStream_t st) {
+  return g_conv_f16 ? launch_convt_impl<TZ, T, NPAD, MT, 2, true>(p, st) : launch_convt_impl<TZ, T, NPAD, MT, 2, false>(p, st);
 }
 
 }  // namespace gb
@@ -427,6 +489,44 @@ extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const v
   if (T == 4 && npad == 64 && W == 16) GB_CT(4, 64, 2);
 #undef GB_CT
   return fail_arg(GENRE_B200_EINVAL, "convt3d: no kernel instance for k=%d npad=%d W=%lld", ksize, npad, (long long)W);
+}
+
+// ConvTranspose3d(kernel 8, stride 2, padding 3) with the four (y,x) output parity classes merged along N (kernel MODE 2):
+// the layer that dominates Unet_3D, dec5 = ConvT(80 -> 20) on 32^3 (networks/networks.py:166).  Same operands as
+// genre_b200_convt3d_s2_forward except
+//   wpack [2 z-parity][4 z-tap][Cin chunk][5*5 union taps][2][npad/8][8][g], npad = 4 * cpad columns ordered
+//         n = (py*2+px)*cpad + co  (ops_conv.pack_convt_merged_weights);  scale, shift [cpad].
+// Supported: ksize 8, npad = 80 (Cout <= 20), W in {16, 32}, H % 16 == 0.
+extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
+                                                    int64_t D, int64_t H, int64_t W, const void *wpack_, int ksize,
+                                                    int npad, int f16, const float *scale, const float *shift,
+                                                    float slope, float *out, int cgo, void *stream) {
+  const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
+  g_conv_f16 = f16 != 0;
+  GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "convt3d_merged: null pointer");
+  GB_REQUIRE(ksize == 8, GENRE_B200_EINVAL, "convt3d_merged: kernel size %d unsupported (8)", ksize);
+  GB_REQUIRE(npad == 80, GENRE_B200_EINVAL, "convt3d_merged: npad %d unsupported (80 = 4 classes x 20 channels)", npad);
+  GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "convt3d_merged: input width %lld unsupported (16 or 32)", (long long)W);
+  GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt3d_merged: bad extent");
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && cg0 % CT_KCG == 0 && cg1 % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "convt3d_merged: channel groups (%d, %d) must be even", cg0, cg1);
+  GB_REQUIRE(cgo > 0 && 16 * cgo <= npad, GENRE_B200_EINVAL, "convt3d_merged: %d output channels exceed npad/4", 4 * cgo);
+  GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "convt3d_merged: grid too large");
+  GB_REQUIRE(aligned16(src0) && aligned16(wpack) && aligned16(out) && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,
+             "convt3d_merged: buffers must be 16-byte aligned");
+  ConvTParams p;
+  p.src0 = src0; p.src1 = src1; p.cg0 = cg0; p.cg1 = cg1;
+  p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
+  p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  p.srcpar_cgs = 0;
+  const int pad = ksize / 2 - 1;
+  for (int par = 0; par < 2; ++par) {
+    const int k0 = (par + pad) % 2;
+    p.base[par] = (par + pad - k0) / 2;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (W == 32) return launch_convt_merged<4, 5, 80, 4>(p, st);
+  return launch_convt_merged<4, 5, 80, 2>(p, st);
 }
 
 // Stride-1 convolution with T taps per dimension on channel-blocked activations (same kernel, one output class):

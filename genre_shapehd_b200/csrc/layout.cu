@@ -1,0 +1,202 @@
+// layout.cu — NCDHW <-> channel-blocked activation layouts for the tcgen05 convolution kernels (convt3d.cu).
+//
+// The reference's nets (networks/networks.py) exchange NCDHW fp32 tensors; the kernels want 16 bytes per position and
+// channel group ([B*D][C/g][H][W][g], g = 4 fp32 or 8 fp16) so that a tap shift is an address offset.  These are the
+// boundary crossings, each ONE pass over the data: every warp load is a contiguous run along x of one channel plane,
+// every store is 16 bytes per thread, contiguous across the warp.  Pure HBM-bound byte moves.
+//   to_blocked    : [B,C,D,H,W] fp32            -> [B*D][C/g][H][W][g]                      (cast to fp16 when g = 8)
+//   s2d_blocked   : [B,C,D,H,W] fp32 (even ext) -> [B*D/2][8C/g][H/2][W/2][g], channel = ((c*2+pz)*2+py)*2+px
+//   s2d_sources   : [B,C,D,H,W] fp32 (even ext) -> [B*D/2][8*cpad/g][H/2][W/2][g], the 8 parity sub-volumes one after
+//                   the other along the channel-group axis, each zero-padded from C to cpad channels
+//   from_blocked  : [B*D][cg][H][W][4] fp32     -> [B,C,D,H,W] fp32 (drops channel padding)
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int LY_THREADS = 256;
+
+template <int G>
+__device__ __forceinline__ void store_unit(void *dst, size_t unit_index, const float (&x)[G]) {
+  if (G == 4) {
+    reinterpret_cast<float4 *>(dst)[unit_index] = make_float4(x[0], x[1], x[2], x[3]);
+  } else {
+    const __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
+    const __half2 c = __floats2half2_rn(x[4 % G], x[5 % G]), d = __floats2half2_rn(x[6 % G], x[7 % G]);
+    uint4 u;
+    u.x = *reinterpret_cast<const unsigned *>(&a);
+    u.y = *reinterpret_cast<const unsigned *>(&b);
+    u.z = *reinterpret_cast<const unsigned *>(&c);
+    u.w = *reinterpret_cast<const unsigned *>(&d);
+    reinterpret_cast<uint4 *>(dst)[unit_index] = u;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(LY_THREADS)
+to_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t units) {
+  const int CG = C / G;
+  const size_t plane = (size_t)H * W, vol = plane * D;
+  for (size_t u = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; u < units; u += (size_t)gridDim.x * LY_THREADS) {
+    const size_t hw = u % plane;
+    size_t r = u / plane;
+    const int cg = (int)(r % CG);
+    r /= CG;  // b * D + d
+    const size_t b = r / D, d = r - b * D;
+    const float *s = src + ((b * C + (size_t)cg * G) * D + d) * plane + hw;
+    float x[G];
+#pragma unroll
+    for (int e = 0; e < G; ++e) x[e] = __ldg(s + e * vol);
+    store_unit<G>(dst, u, x);
+  }
+}
+
+// one thread = one output position (z', y', x') of one input channel c: reads the 2x2x2 cell as four float2
+template <int G>
+__global__ void __launch_bounds__(LY_THREADS)
+s2d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t cells) {
+  const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
+  const int CGo = C * 8 / G;
+  for (size_t i = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; i < cells; i += (size_t)gridDim.x * LY_THREADS) {
+    const int x2 = (int)(i % W2);
+    size_t r = i / W2;
+    const int y2 = (int)(r % H2);
+    r /= H2;
+    const int c = (int)(r % C);
+    r /= C;  // b * D2 + z'
+    const size_t b = r / D2, z2 = r - b * D2;
+    const float *s = src + (((b * C + c) * D + 2 * z2) * H + 2 * y2) * (size_t)W + 2 * x2;
+    float v[8];
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(s + ((size_t)pz * H + py) * W));
+        v[(pz * 2 + py) * 2] = t.x;
+        v[(pz * 2 + py) * 2 + 1] = t.y;
+      }
+    if (G == 8) {
+      float x[G];
+#pragma unroll
+      for (int e = 0; e < G; ++e) x[e] = v[e % 8];
+      store_unit<G>(dst, ((r * CGo + c) * H2 + y2) * (size_t)W2 + x2, x);
+    } else {
+#pragma unroll
+      for (int pz = 0; pz < 2; ++pz) {
+        float x[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) x[e] = v[(pz * 4 + e) % 8];
+        store_unit<G>(dst, ((r * CGo + c * 2 + pz) * H2 + y2) * (size_t)W2 + x2, x);
+      }
+    }
+  }
+}
+
+// one thread = (z', pz, py, channel group, y', x'): reads G float2 (both x parities), writes the px = 0 and 1 units
+template <int G>
+__global__ void __launch_bounds__(LY_THREADS)
+s2d_sources_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int cpad, int D, int H, int W,
+                   size_t items) {
+  const int D2 = D / 2, H2 = H / 2, W2 = W / 2, CGs = cpad / G;
+  const size_t vol = (size_t)D * H * W;
+  for (size_t i = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; i < items; i += (size_t)gridDim.x * LY_THREADS) {
+    const int x2 = (int)(i % W2);
+    size_t r = i / W2;
+    const int y2 = (int)(r % H2);
+    r /= H2;
+    const int cg = (int)(r % CGs);
+    r /= CGs;
+    const int pzy = (int)(r & 3);
+    r >>= 2;  // b * D2 + z'
+    const size_t b = r / D2, z2 = r - b * D2;
+    const int pz = pzy >> 1, py = pzy & 1;
+    const float *s = src + (((b * C + (size_t)cg * G) * D + 2 * z2 + pz) * H + 2 * y2 + py) * (size_t)W + 2 * x2;
+    float x0[G], x1[G];
+#pragma unroll
+    for (int e = 0; e < G; ++e) {
+      float2 t = make_float2(0.f, 0.f);
+      if (cg * G + e < C) t = __ldg(reinterpret_cast<const float2 *>(s + e * vol));
+      x0[e] = t.x;
+      x1[e] = t.y;
+    }
+    const size_t u = ((r * (8 * CGs) + (size_t)(pzy * 2) * CGs + cg) * H2 + y2) * (size_t)W2 + x2;
+    store_unit<G>(dst, u, x0);
+    store_unit<G>(dst, u + (size_t)CGs * H2 * W2, x1);
+  }
+}
+
+__global__ void __launch_bounds__(LY_THREADS)
+from_blocked_kernel(const float4 *__restrict__ src, float *__restrict__ dst, int C, int CG, int D, int H, int W,
+                    size_t units) {
+  const size_t plane = (size_t)H * W, vol = plane * D;
+  for (size_t u = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; u < units; u += (size_t)gridDim.x * LY_THREADS) {
+    const size_t hw = u % plane;
+    size_t r = u / plane;
+    const int cg = (int)(r % CG);
+    r /= CG;
+    const size_t b = r / D, d = r - b * D;
+    const float4 v = __ldg(src + u);
+    float *o = dst + ((b * C + (size_t)cg * 4) * D + d) * plane + hw;
+    const int c0 = cg * 4;
+    if (c0 + 0 < C) o[0] = v.x;
+    if (c0 + 1 < C) o[vol] = v.y;
+    if (c0 + 2 < C) o[2 * vol] = v.z;
+    if (c0 + 3 < C) o[3 * vol] = v.w;
+  }
+}
+
+static unsigned ly_grid(size_t n) {
+  const size_t blocks = (n + LY_THREADS - 1) / LY_THREADS;
+  const size_t cap = 148ull * 8 * 16;  // grid-stride beyond ~16 waves of 8 CTAs per SM
+  return (unsigned)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+// mode 0: to_blocked, 1: s2d_blocked, 2: s2d_sources (cpad = padded channels per sub-volume; ignored otherwise).
+// group 4 -> fp32 units, 8 -> fp16 units.  src is contiguous NCDHW fp32.
+extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
+                                           int mode, int group, int cpad, void *dst, void *stream) {
+  GB_REQUIRE(src && dst, GENRE_B200_EINVAL, "to_blocked: null pointer");
+  GB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, GENRE_B200_EINVAL, "to_blocked: empty tensor");
+  GB_REQUIRE(group == 4 || group == 8, GENRE_B200_EINVAL, "to_blocked: group must be 4 (fp32) or 8 (fp16)");
+  GB_REQUIRE(aligned16(dst), GENRE_B200_EALIGN, "to_blocked: dst must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  if (mode == 0) {
+    GB_REQUIRE(C % group == 0, GENRE_B200_EINVAL, "to_blocked: C=%lld not a multiple of %d", (long long)C, group);
+    const size_t units = (size_t)(B * D * (C / group) * H * W);
+    if (group == 4) to_blocked_kernel<4><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
+    else to_blocked_kernel<8><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
+    return check_launch("to_blocked kernel");
+  }
+  GB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, GENRE_B200_EINVAL, "space-to-depth: odd extent");
+  GB_REQUIRE(((uintptr_t)src & 7) == 0, GENRE_B200_EALIGN, "space-to-depth: src must be 8-byte aligned");
+  if (mode == 1) {
+    const size_t cells = (size_t)(B * C * (D / 2) * (H / 2) * (W / 2));
+    if (group == 4) s2d_blocked_kernel<4><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells);
+    else s2d_blocked_kernel<8><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells);
+    return check_launch("s2d_blocked kernel");
+  }
+  GB_REQUIRE(mode == 2, GENRE_B200_EINVAL, "to_blocked: unknown mode %d", mode);
+  GB_REQUIRE(cpad >= C && cpad % group == 0, GENRE_B200_EINVAL, "s2d_sources: cpad=%d must be >= C and a multiple of %d", cpad, group);
+  const size_t items = (size_t)(B * (D / 2) * 4 * (cpad / group) * (H / 2) * (W / 2));
+  if (group == 4) s2d_sources_kernel<4><<<ly_grid(items), LY_THREADS, 0, st>>>(src, dst, (int)C, cpad, (int)D, (int)H, (int)W, items);
+  else s2d_sources_kernel<8><<<ly_grid(items), LY_THREADS, 0, st>>>(src, dst, (int)C, cpad, (int)D, (int)H, (int)W, items);
+  return check_launch("s2d_sources kernel");
+}
+
+// blocked fp32 [B*D][cg][H][W][4] -> contiguous NCDHW [B,C,D,H,W] (C <= 4*cg)
+extern "C" int genre_b200_blocked_to_ncdhw(const float *src, int cg, int64_t B, int64_t C, int64_t D, int64_t H,
+                                           int64_t W, float *dst, void *stream) {
+  GB_REQUIRE(src && dst, GENRE_B200_EINVAL, "from_blocked: null pointer");
+  GB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0 && cg > 0 && C <= 4 * (int64_t)cg && C > 4 * (int64_t)(cg - 1),
+             GENRE_B200_EINVAL, "from_blocked: bad shape (C=%lld, cg=%d)", (long long)C, cg);
+  GB_REQUIRE(aligned16(src), GENRE_B200_EALIGN, "from_blocked: src must be 16-byte aligned");
+  const size_t units = (size_t)(B * D * cg * H * W);
+  from_blocked_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, dst, (int)C, cg, (int)D,
+                                                                           (int)H, (int)W, units);
+  return check_launch("from_blocked kernel");
+}

@@ -39,6 +39,8 @@ K4S2_MIN_CIN = 8
 # mantissa as TF32 with half the operand bytes (the kernels are bound by shared-memory operand bandwidth, so ~2x
 # faster); "tf32" = fp32 storage read as TF32.  Both accumulate in fp32 and produce fp32 activations.
 PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "f16")
+# k=8 ConvTranspose3d with Cout <= 20 (Unet_3D.dec5): merge the four (y,x) parity classes into one N=80 MMA stream
+MERGE_PARITIES = os.environ.get("GENRE_B200_CONV_MERGE", "1") != "0"
 
 
 def _f16():
@@ -50,12 +52,28 @@ def _group():
     return 8 if _f16() else 4
 
 
+def _on_device(x, group, dtype):
+    """the CUDA layout kernels (csrc/layout.cu) take contiguous fp32 NCDHW and write fp32 groups of 4 or fp16 groups of 8"""
+    return (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+            and ((group == 4 and dtype in (None, torch.float32)) or (group == 8 and dtype == torch.float16)))
+
+
+def _permuted_copy(view, dtype):
+    """materialise a permuted view in ONE pass, the cast (if any) riding on the copy"""
+    out = torch.empty(view.shape, device=view.device, dtype=dtype or view.dtype)
+    out.copy_(view)
+    return out
+
+
 def to_blocked(x, group=4, dtype=None):
     """NCDHW [B,C,D,H,W] (C % group == 0) -> [B*D, C/group, H, W, group] contiguous (optionally cast)."""
     b, c, d, h, w = x.shape
-    if dtype is not None and x.dtype != dtype:
-        x = x.to(dtype)
-    return x.reshape(b, c // group, group, d, h, w).permute(0, 3, 1, 4, 5, 2).contiguous().view(b * d, c // group, h, w, group)
+    if _on_device(x, group, dtype):
+        out = torch.empty((b * d, c // group, h, w, group), device=x.device, dtype=dtype or x.dtype)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 0, group, 0, out.data_ptr(), _lib.stream_ptr(x))
+        return out
+    v = x.reshape(b, c // group, group, d, h, w).permute(0, 3, 1, 4, 5, 2)
+    return _permuted_copy(v, dtype).view(b * d, c // group, h, w, group)
 
 
 def _to_operand(x):
@@ -67,7 +85,11 @@ def from_blocked(y, batch, channels):
     the result so that a following custom layer can consume it without converting back."""
     bd, cg, h, w, _ = y.shape
     d = bd // batch
-    out = y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
+    if y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and 4 * (cg - 1) < channels:
+        out = torch.empty((batch, channels, d, h, w), device=y.device, dtype=torch.float32)
+        _lib.call("genre_b200_blocked_to_ncdhw", y.data_ptr(), cg, batch, channels, d, h, w, out.data_ptr(), _lib.stream_ptr(y))
+    else:
+        out = y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
     out._gb_blocked = y
     return out
 
@@ -99,6 +121,35 @@ def pack_convt_weights(weight, npad, group=4):
                 sub = sub.reshape(cin // (2 * g), 2, g, npad // 8, 8, t, t, t)        # (kc, kk, e, ng, r, tz, ty, tx)
                 out[pz, py, px] = sub.permute(5, 0, 6, 7, 1, 3, 4, 2)                 # (tz, kc, ty, tx, kk, ng, r, e)
     out = out.contiguous()
+    return out.half() if g == 8 else out
+
+
+def pack_convt_merged_weights(weight, cpad, group=4):
+    """ConvTranspose3d weight [Cin, Cout, K, K, K] (stride 2, padding K/2-1) for the merged-parity kernel (MODE 2):
+    [2 z-parity][T z-tap][Cin/(2g) chunk][(T+1)^2 union (y,x) taps][2 k-core][N/8][8][g],  N = 4*cpad, column
+    n = (py*2+px)*cpad + co.  Union tap u reads input j + T/2 - u; class p uses it as its tap t = u - 1 + p (k = k0_p + 2t)
+    when 0 <= t < T, and holds zeros otherwise."""
+    cin, cout, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    t, pad, g = k // 2, k // 2 - 1, group
+    tu, n = t + 1, 4 * cpad
+    k0 = [(p + pad) % 2 for p in (0, 1)]
+    weq = weight.new_zeros((cin, n, 2, t, tu, tu))                       # (ci, n, pz, tz, uy, ux)
+    for py in (0, 1):
+        for px in (0, 1):
+            c0 = (py * 2 + px) * cpad
+            for uy in range(tu):
+                ty = uy - 1 + py
+                if not 0 <= ty < t:
+                    continue
+                for ux in range(tu):
+                    tx = ux - 1 + px
+                    if not 0 <= tx < t:
+                        continue
+                    for pz in (0, 1):
+                        # [Cin, Cout, tz]
+                        weq[:, c0:c0 + cout, pz, :, uy, ux] = weight[:, :, k0[pz]::2, k0[py] + 2 * ty, k0[px] + 2 * tx]
+    sub = weq.reshape(cin // (2 * g), 2, g, n // 8, 8, 2, t, tu, tu)    # (kc, kk, e, ng, r, pz, tz, uy, ux)
+    out = sub.permute(5, 6, 0, 7, 8, 1, 3, 4, 2).contiguous()           # (pz, tz, kc, uy, ux, kk, ng, r, e)
     return out.half() if g == 8 else out
 
 
@@ -139,8 +190,21 @@ def convt3d_s2_blocked(src0, src1, batch, module, scale=None, shift=None, slope=
     cout = module.out_channels
     npad = 32 if cout <= 32 else 64
     cgo = (cout + 3) // 4
-    wpack = _packed(module, npad)
     dev = src0.device
+    if MERGE_PARITIES and module.kernel_size[0] == 8 and cout <= 20:
+        # the four (y,x) parity classes share one MMA stream: N = 4 x 20 columns (csrc/convt3d.cu MODE 2)
+        g = 8 if src0.dtype == torch.float16 else 4
+        wpack = _cached_pack(module, ("convt_merged", 20, g), lambda wt: pack_convt_merged_weights(wt, 20, g))
+        sc = torch.ones(20, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, 20 - cout), value=1.0)
+        if shift is None:
+            shift = module.bias.detach() if module.bias is not None else torch.zeros(cout, device=dev)
+        sh = torch.nn.functional.pad(shift.float(), (0, 20 - cout))
+        out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=dev, dtype=torch.float32)
+        _lib.call("genre_b200_convt3d_s2_merged_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
+                  cg1, batch, bd // batch, h, w, wpack.data_ptr(), 8, 80, 1 if g == 8 else 0, sc.data_ptr(), sh.data_ptr(),
+                  float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
+        return out
+    wpack = _packed(module, npad)
     sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
     if shift is None:
         shift = module.bias.detach() if module.bias is not None else torch.zeros(cout, device=dev)
@@ -161,14 +225,22 @@ def _no_autograd(*tensors):
 
 
 def space_to_depth_blocked(x, group=4, dtype=None):
-    """NCDHW [B,C,D,H,W] (even extents, C*8 % group == 0) -> blocked [B*D/2, C*8/group, H/2, W/2, group] whose channel
+    """NCDHW [B,C,D,H,W] (even extents, group | 8) -> blocked [B*D/2, C*8/group, H/2, W/2, group] whose channel
     index is ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px)."""
     b, c, d, h, w = x.shape
-    if dtype is not None and x.dtype != dtype:
-        x = x.to(dtype)
-    t = x.reshape(b, c, d // 2, 2, h // 2, 2, w // 2, 2).permute(0, 2, 1, 3, 5, 7, 4, 6)   # b z' c pz py px y' x'
-    t = t.reshape(b * (d // 2), (c * 8) // group, group, h // 2, w // 2).permute(0, 1, 3, 4, 2)
-    return t.contiguous()
+    assert 8 % group == 0
+    if _on_device(x, group, dtype):
+        out = torch.empty((b * (d // 2), c * 8 // group, h // 2, w // 2, group), device=x.device, dtype=dtype or x.dtype)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 1, group, 0, out.data_ptr(), _lib.stream_ptr(x))
+        return out
+    s = 8 // group                                       # channel groups per input channel
+    # pz,py,px bits split as (j, e) with j the top log2(s) bits: view dims b c z' pz y' py x' px
+    t = x.reshape(b, c, d // 2, 2, h // 2, 2, w // 2, 2)
+    if s == 1:      # e = (pz,py,px)
+        v = t.permute(0, 2, 1, 4, 6, 3, 5, 7)            # b z' c y' x' pz py px
+    else:           # s == 2: j = pz, e = (py,px)
+        v = t.permute(0, 2, 1, 3, 4, 6, 5, 7)            # b z' c pz y' x' py px
+    return _permuted_copy(v, dtype).view(b * (d // 2), c * s, h // 2, w // 2, group)
 
 
 def pack_conv_k8s2_weights(weight, npad, group=4):
@@ -217,13 +289,15 @@ def space_to_depth_sources(x, cpad, group, dtype):
     other along the channel-group axis (sub-volume s = (pz*2+py)*2+px holds in[2z'+pz, 2y'+py, 2x'+px]), each zero-padded
     from C to cpad channels."""
     b, c, d, h, w = x.shape
-    if dtype is not None and x.dtype != dtype:
-        x = x.to(dtype)
+    if _on_device(x, group, dtype):
+        out = torch.empty((b * (d // 2), 8 * (cpad // group), h // 2, w // 2, group), device=x.device, dtype=dtype or x.dtype)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 2, group, cpad, out.data_ptr(), _lib.stream_ptr(x))
+        return out
     if cpad != c:
         x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 0, 0, cpad - c))
     t = x.reshape(b, cpad // group, group, d // 2, 2, h // 2, 2, w // 2, 2)      # b cg e z' pz y' py x' px
-    t = t.permute(0, 3, 4, 6, 8, 1, 5, 7, 2)                                      # b z' pz py px cg y' x' e
-    return t.reshape(b * (d // 2), 8 * (cpad // group), h // 2, w // 2, group).contiguous()
+    v = t.permute(0, 3, 4, 6, 8, 1, 5, 7, 2)                                      # b z' pz py px cg y' x' e
+    return _permuted_copy(v, dtype).view(b * (d // 2), 8 * (cpad // group), h // 2, w // 2, group)
 
 
 def pack_conv_k4s2_weights(weight, cpad, npad, group):

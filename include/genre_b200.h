@@ -217,6 +217,28 @@ int genre_b200_convt_c1_forward(const float *src0, int cg0, const float *src1, i
                                 int64_t B, int64_t D, int64_t H, int64_t W,
                                 const float *weight, float bias, int act_sigmoid, float *out, void *stream);
 
+/* ConvTranspose3d(k 8, s 2, p 3), Cout <= 20, with the four (y,x) output parity classes merged along N (one N = 80 MMA
+ * over the union of 5x5 taps instead of four N = 20 MMAs over 4x4): Unet_3D.dec5 = ConvT(80 -> 20) (networks/networks.py:166),
+ * 53.7 of the refiner's 78 GFLOP.  Operands as genre_b200_convt3d_s2_forward except wpack
+ * [2 z-parity][4][Cin chunk][25][2][npad/8][8][g] with npad = 80 columns n = (py*2+px)*20 + co; scale, shift [20]. */
+int genre_b200_convt3d_s2_merged_forward(const void *src0, int cg0, const void *src1, int cg1,
+                                         int64_t B, int64_t D, int64_t H, int64_t W,
+                                         const void *wpack, int ksize, int npad, int f16,
+                                         const float *scale, const float *shift, float slope,
+                                         float *out, int cgo, void *stream);
+
+/* Layout boundary of the convolution kernels: contiguous NCDHW fp32 (what networks/networks.py's modules exchange,
+ * e.g. Unet_3D.forward networks.py:170-190) <-> channel-blocked [B*D][C/g][H][W][g] (16 bytes per unit).
+ *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1);
+ *   mode 2: the 8 parity sub-volumes one after the other, each padded to cpad channels (Conv3d k4 s2).
+ *   group 4: fp32 units, group 8: fp16 units (cast on the way).  One pass, 16-byte stores. */
+int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
+                                int mode, int group, int cpad, void *dst, void *stream);
+
+/* blocked fp32 [B*D][cg][H][W][4] -> contiguous NCDHW [B,C,D,H,W], 4*(cg-1) < C <= 4*cg (channel padding dropped) */
+int genre_b200_blocked_to_ncdhw(const float *src, int cg, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
+                                float *dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

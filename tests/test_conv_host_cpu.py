@@ -1,0 +1,115 @@
+"""Host side of the tcgen05 convolution path on CPU: the weight packers and layout transforms of
+genre_shapehd_b200/ops_conv.py define, together with the kernel's tap geometry (csrc/convt3d.cu: input = j + base - t),
+a plain sum of shifted matrix products.  That sum is emulated here in torch and compared with torch's own
+conv_transpose3d / conv3d (networks/networks.py:40-57,151-167 layers), so a packing bug is caught without a GPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from genre_shapehd_b200 import ops_conv
+
+
+def _shift(x, dz, dy, dx):
+    """x [B,D,H,W,C] -> y[b,z,y,x] = x[b,z+dz,y+dy,x+dx] (zero outside)"""
+    b, d, h, w, c = x.shape
+    m = max(abs(dz), abs(dy), abs(dx))
+    xp = F.pad(x, (0, 0, m, m, m, m, m, m))
+    return xp[:, m + dz:m + dz + d, m + dy:m + dy + h, m + dx:m + dx + w]
+
+
+def _taps_gemm(xb, batch, wp, bz, by, bx):
+    """xb blocked [B*D,CG,H,W,g]; wp [TZ][nchunk][TY][TX][2][N/8][8][g] -> [B,D,H,W,N]"""
+    bd, cg, h, w, g = xb.shape
+    x = xb.view(batch, bd // batch, cg, h, w, g).permute(0, 1, 3, 4, 2, 5).reshape(batch, bd // batch, h, w, cg * g).double()
+    tz_n, nchunk, ty_n, tx_n = wp.shape[:4]
+    n = wp.shape[5] * 8
+    out = torch.zeros(batch, bd // batch, h, w, n, dtype=torch.float64)
+    for tz in range(tz_n):
+        for ty in range(ty_n):
+            for tx in range(tx_n):
+                wm = wp[tz, :, ty, tx].permute(0, 1, 4, 2, 3).reshape(nchunk * 2 * g, n).double()   # (kc,kk,e | ng,r)
+                out += _shift(x, bz - tz, by - ty, bx - tx) @ wm
+    return out
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_pack_convt_weights_parity_classes(k):
+    torch.manual_seed(k)
+    cin, cout, npad = 8, 5, 8
+    wt = torch.randn(cin, cout, k, k, k)
+    x = torch.randn(2, cin, 3, 4, 5)
+    ref = F.conv_transpose3d(x.double(), wt.double(), stride=2, padding=k // 2 - 1)
+    wp = ops_conv.pack_convt_weights(wt, npad, 4)
+    xb = ops_conv.to_blocked(x, 4)
+    pad = k // 2 - 1
+    base = [(p + pad - (p + pad) % 2) // 2 for p in (0, 1)]
+    out = torch.zeros_like(ref)
+    for pz in (0, 1):
+        for py in (0, 1):
+            for px in (0, 1):
+                y = _taps_gemm(xb, 2, wp[pz, py, px], base[pz], base[py], base[px])[..., :cout]
+                out[:, :, pz::2, py::2, px::2] = y.permute(0, 4, 1, 2, 3)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_pack_convt_merged_weights(k):
+    torch.manual_seed(10 + k)
+    cin, cout, cpad = 8, 5, 8
+    wt = torch.randn(cin, cout, k, k, k)
+    x = torch.randn(2, cin, 3, 4, 5)
+    ref = F.conv_transpose3d(x.double(), wt.double(), stride=2, padding=k // 2 - 1)
+    wp = ops_conv.pack_convt_merged_weights(wt, cpad, 4)        # [2][T][nchunk][T+1][T+1][2][N/8][8][4]
+    assert wp.shape[:5] == (2, k // 2, 1, k // 2 + 1, k // 2 + 1) and wp.shape[6] * 8 == 4 * cpad
+    xb = ops_conv.to_blocked(x, 4)
+    pad, t = k // 2 - 1, k // 2
+    base = [(p + pad - (p + pad) % 2) // 2 for p in (0, 1)]
+    out = torch.zeros_like(ref)
+    for pz in (0, 1):
+        y = _taps_gemm(xb, 2, wp[pz], base[pz], t // 2, t // 2)                         # [B,D,H,W,4*cpad]
+        for py in (0, 1):
+            for px in (0, 1):
+                c0 = (py * 2 + px) * cpad
+                out[:, :, pz::2, py::2, px::2] = y[..., c0:c0 + cout].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_pack_conv_k8s2_weights_space_to_depth():
+    torch.manual_seed(3)
+    cin, cout, npad = 2, 5, 8
+    wt = torch.randn(cout, cin, 8, 8, 8)
+    x = torch.randn(2, cin, 4, 6, 8)
+    ref = F.conv3d(x.double(), wt.double(), stride=2, padding=3)
+    wp = ops_conv.pack_conv_k8s2_weights(wt, npad, 4)
+    xb = ops_conv.space_to_depth_blocked(x, 4)
+    y = _taps_gemm(xb, 2, wp, 2, 2, 2)[..., :cout].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(y, ref, atol=1e-5)
+
+
+def test_pack_conv_k4s2_weights_parity_sources():
+    torch.manual_seed(4)
+    cin, cout, cpad, npad, g = 5, 6, 8, 8, 4
+    wt = torch.randn(cout, cin, 4, 4, 4)
+    x = torch.randn(2, cin, 4, 6, 8)
+    ref = F.conv3d(x.double(), wt.double(), stride=2, padding=1)
+    wp = ops_conv.pack_conv_k4s2_weights(wt, cpad, npad, g)     # [2][8*cpad/(2g)][2][2][2][npad/8][8][g]
+    xb = ops_conv.space_to_depth_sources(x, cpad, g, None)      # [B*D', 8*cpad/g, H', W', g]
+    cgs = cpad // g
+    out = torch.zeros_like(ref)
+    for s in range(8):                                          # sub-volume s is a K range with base 1 - p per dim
+        pz, py, px = (s >> 2) & 1, (s >> 1) & 1, s & 1
+        kc0, kc1 = s * cgs // 2, (s + 1) * cgs // 2
+        y = _taps_gemm(xb[:, s * cgs:(s + 1) * cgs].contiguous(), 2, wp[:, kc0:kc1], 1 - pz, 1 - py, 1 - px)
+        out += y[..., :cout].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("group", [4, 8])
+def test_space_to_depth_channel_order(group):
+    x = torch.arange(2 * 2 * 4 * 4 * 4, dtype=torch.float32).reshape(2, 2, 4, 4, 4)
+    y = ops_conv.space_to_depth_blocked(x, group)
+    bd, cg, h, w, g = y.shape
+    assert (bd, cg * g, h, w) == (4, 16, 2, 2)
+    for ch in range(16):
+        c, pz, py, px = ch // 8, (ch // 4) % 2, (ch // 2) % 2, ch % 2
+        assert torch.equal(y[2:, ch // g, :, :, ch % g], x[1, c, pz::2, py::2, px::2])

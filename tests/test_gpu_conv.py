@@ -46,10 +46,51 @@ def test_convt3d_vs_torch(k, cin, cout, b, d, h, w):
     assert err <= 4e-3 * scale, "max err %g vs scale %g" % (err, scale)   # TF32 operands (10-bit mantissa)
 
 
+@pytest.mark.parametrize("cin,cout,b,d,h,w", [(16, 20, 1, 2, 16, 16), (80, 20, 2, 3, 32, 32), (32, 7, 1, 1, 16, 32)])
+def test_convt_k8_merged_parities_vs_separate_and_torch(cin, cout, b, d, h, w):
+    """MODE 2 (four (y,x) parity classes in one N=80 MMA stream) against the per-class kernel and torch"""
+    torch.manual_seed(cin + cout)
+    m = nets.ConvTranspose3d(cin, cout, 8, 2, 3).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV)
+    old = ops_conv.MERGE_PARITIES
+    try:
+        with torch.no_grad():
+            ops_conv.MERGE_PARITIES = True
+            ym = ops_conv.conv_transpose3d(x, m)
+            ops_conv.MERGE_PARITIES = False
+            ys = ops_conv.conv_transpose3d(x, m)
+            ref = _ref(x, m)
+    finally:
+        ops_conv.MERGE_PARITIES = old
+    assert ym is not None and ys is not None
+    scale = ref.abs().max().item()
+    assert (ym - ref).abs().max().item() <= 4e-3 * scale
+    # same products, same fp32 accumulator; only the order of the K walk differs
+    assert (ym - ys).abs().max().item() <= 1e-4 * scale
+
+
 def test_blocked_layout_roundtrip():
     x = torch.randn(2, 24, 3, 16, 16, device=DEV)
     assert torch.equal(ops_conv.from_blocked(ops_conv.to_blocked(x), 2, 24), x)
     assert ops_conv.to_blocked(x, 8, torch.float16).shape == (6, 3, 16, 16, 8)
+
+
+@pytest.mark.parametrize("group,dtype", [(4, None), (8, torch.float16)])
+def test_layout_kernels_match_torch_permutes(group, dtype):
+    """csrc/layout.cu against the torch permute formulation of the same layouts (bit-exact: pure moves / one rounding)"""
+    torch.manual_seed(11)
+    x = torch.randn(2, 16, 6, 10, 12, device=DEV)
+    xc = x.cpu()
+    assert torch.equal(ops_conv.to_blocked(x, group, dtype).cpu(), ops_conv.to_blocked(xc, group, dtype))
+    x2 = torch.randn(3, 2, 4, 6, 8, device=DEV)
+    assert torch.equal(ops_conv.space_to_depth_blocked(x2, group, dtype).cpu(),
+                       ops_conv.space_to_depth_blocked(x2.cpu(), group, dtype))
+    x3 = torch.randn(2, 5, 4, 6, 8, device=DEV)           # 5 channels padded to 8 / 16 per sub-volume
+    for cpad in (8, 16):
+        assert torch.equal(ops_conv.space_to_depth_sources(x3, cpad, group, dtype).cpu(),
+                           ops_conv.space_to_depth_sources(x3.cpu(), cpad, group, dtype))
+    y = torch.randn(2 * 3, 5, 7, 9, 4, device=DEV)        # 5 groups = 20 padded channels, 18 real
+    assert torch.equal(ops_conv.from_blocked(y, 2, 18).cpu(), ops_conv.from_blocked(y.cpu(), 2, 18))
 
 
 def test_deconv_skip_fused_bn_leaky_vs_torch():
