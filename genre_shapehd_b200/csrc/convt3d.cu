@@ -40,6 +40,7 @@ struct ConvTParams {
   float *out;                // blocked [B*2D][cgo][2H][2W][4]
   int cgo;                   // output channel groups
   int base[2];               // input index = j + base[par] - t
+  int xtiles;                // the CTA tile is 8*MT positions wide; W = xtiles * 8 * MT (set by the launcher)
   int srcpar_cgs;            // 0, or: the K range is 8 parity sub-volumes of srcpar_cgs channel groups each (strided
                              // Conv3d k=4 s=2 p=1 after space-to-depth); sub-volume s = (pz,py,px) uses base 1 - p per dim
 };
@@ -181,11 +182,15 @@ struct ConvTCfg {
 //         does not use a tap) replaces four N = Cout MMAs.  An M128 MMA costs about the same 64+ cycles for any
 //         N <= 128 (the A operand streams from shared memory at a fixed rate), so this is ~2.5x fewer tensor cycles.
 //         TZ = K/2 z taps of the CTA's z parity.
+// MODE 3: a stride-1 T-tap convolution whose N columns are the 8 output classes of a 2x upsampled grid
+//         (n = ((qz*2+qy)*2+qx)*Cout + co, written to output position 2*j + q): a strided Conv3d(k 8, s 2, p 3) on
+//         a 4x space-to-depth input (Unet_3D.enc1: 2 -> 128 channels, 3 taps, N = 8 x 20) - the same "few wide
+//         MMAs instead of many narrow ones" trade as MODE 2, for a forward convolution.
 template <int TZ, int T, int NPAD, int MT, int MODE, bool F16>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 convt3d_s2_kernel(const ConvTParams p) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
-  constexpr bool PAR = MODE == 0, MERGE = MODE == 2;
+  constexpr bool PAR = MODE == 0, MERGE = MODE == 2, MERGE8 = MODE == 3;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *stages = smem;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -197,10 +202,12 @@ convt3d_s2_kernel(const ConvTParams p) {
   const int par = blockIdx.y;  // parity class: bit 2 = z, bit 1 = y, bit 0 = x
   const int pz = MERGE ? par : (par >> 2) & 1, py = (par >> 1) & 1, px = par & 1;
   const int ytiles = p.H / CT_BY;
-  const int yt = blockIdx.x % ytiles;
-  const int zj = (blockIdx.x / ytiles) % p.D;
-  const int b = blockIdx.x / (ytiles * p.D);
-  const int y0 = yt * CT_BY;
+  const int xt = blockIdx.x % p.xtiles;
+  const int tile = blockIdx.x / p.xtiles;
+  const int yt = tile % ytiles;
+  const int zj = (tile / ytiles) % p.D;
+  const int b = tile / (ytiles * p.D);
+  const int y0 = yt * CT_BY, x0 = xt * Cfg::W;
   const int nchunk = (p.cg0 + p.cg1) / CT_KCG;
 
   // Stage enumeration shared by the producer and the MMA issuer: q = tz * nchunk + kc, skipped when the z tap plane
@@ -277,7 +284,7 @@ convt3d_s2_kernel(const ConvTParams p) {
         bulk_g2s(sa + Cfg::A_BYTES, wsrc, Cfg::B_BYTES, &full[s]);
       }
       const int zi = zj + bz - tz;
-      const int gy0 = y0 + by - (T - 1), gx0 = bx - (T - 1);  // halo row hy holds input row gy0 + hy
+      const int gy0 = y0 + by - (T - 1), gx0 = x0 + bx - (T - 1);  // halo row hy holds input row gy0 + hy
 #pragma unroll
       for (int c = 0; c < CT_KCG; ++c) {
         int cg = kc * CT_KCG + c;
@@ -303,25 +310,28 @@ convt3d_s2_kernel(const ConvTParams p) {
     tc_fence_after();
     const int m = warp * 32 + lane;  // accumulator row = TMEM lane
     const int yy = m >> 3, xx = m & 7;
-    constexpr bool UP = PAR || MERGE;
+    constexpr bool UP = PAR || MERGE || MERGE8;
     const int Ho = UP ? 2 * p.H : p.H, Wo = UP ? 2 * p.W : p.W, Do = UP ? 2 * p.D : p.D;
-    const int oz = UP ? 2 * zj + pz : zj, oy = PAR ? 2 * (y0 + yy) + py : y0 + yy;
-    if constexpr (MERGE) {
-      constexpr int CP = NPAD / 4;  // output channels per (y,x) parity class
+    const int oz_plain = UP ? 2 * zj + pz : zj, oy = PAR ? 2 * (y0 + yy) + py : y0 + yy;
+    if constexpr (MERGE || MERGE8) {
+      constexpr int NZ = MERGE8 ? 2 : 1;      // z classes held by this CTA's accumulators
+      constexpr int CP = NPAD / (4 * NZ);     // output channels per class
       static_assert(CP % 4 == 0, "merged classes must be whole channel groups");
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int oxb = 2 * (8 * mt + xx);
+        const int oxb = 2 * (x0 + 8 * mt + xx);
 #pragma unroll
-        for (int qy = 0; qy < 2; ++qy) {
+        for (int qzy = 0; qzy < 2 * NZ; ++qzy) {
+          const int qz = MERGE8 ? qzy >> 1 : 0, qy = qzy & 1;
           const int oyy = 2 * (y0 + yy) + qy;
+          const int oz = MERGE8 ? 2 * zj + qz : 2 * zj + pz;
 #pragma unroll
           for (int cgo = 0; cgo < CP / 4; ++cgo) {
             if (cgo >= p.cgo) continue;  // uniform across the CTA
             float v[8];
-            tmem_ld4x2(trow + (uint32_t)(mt * NPAD + (qy * 2) * CP + cgo * 4),
-                       trow + (uint32_t)(mt * NPAD + (qy * 2 + 1) * CP + cgo * 4), v);
+            tmem_ld4x2(trow + (uint32_t)(mt * NPAD + (qzy * 2) * CP + cgo * 4),
+                       trow + (uint32_t)(mt * NPAD + (qzy * 2 + 1) * CP + cgo * 4), v);
             float4 o[2];
 #pragma unroll
             for (int qx = 0; qx < 2; ++qx) {
@@ -342,7 +352,7 @@ convt3d_s2_kernel(const ConvTParams p) {
     } else {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const int ox = PAR ? 2 * (8 * mt + xx) + px : 8 * mt + xx;
+      const int ox = PAR ? 2 * (x0 + 8 * mt + xx) + px : x0 + 8 * mt + xx;
 #pragma unroll
       for (int nb = 0; nb < NPAD / 32; ++nb) {
         float v[32];
@@ -359,7 +369,7 @@ convt3d_s2_kernel(const ConvTParams p) {
               float t = fmaf(v[g4 * 4 + e], __ldg(p.scale + n), __ldg(p.shift + n));
               po[e] = t > 0.0f ? t : t * p.slope;
             }
-            float *dst = p.out + (((((size_t)b * Do + oz) * p.cgo + cgo) * Ho + oy) * (size_t)Wo + ox) * 4;
+            float *dst = p.out + (((((size_t)b * Do + oz_plain) * p.cgo + cgo) * Ho + oy) * (size_t)Wo + ox) * 4;
             *reinterpret_cast<float4 *>(dst) = o;
           }
         }
@@ -423,8 +433,11 @@ static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
     }
     configured[dev & 63] = true;
   }
-  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY)), MODE == 0 ? 8 : MODE == 2 ? 2 : 1);
-  kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(p);
+  ConvTParams q = p;
+  q.xtiles = p.W / Cfg::W;
+  if (q.xtiles < 1 || q.xtiles * Cfg::W != p.W) return fail_arg(GENRE_B200_EINVAL, "convt3d: W=%d is not a multiple of the %d-wide tile", p.W, Cfg::W);
+  dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY) * q.xtiles), MODE == 0 ? 8 : MODE == 2 ? 2 : 1);
+  kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(q);
   return check_launch("convt3d_s2 kernel");
 }
 
@@ -438,6 +451,10 @@ template <int TZ, int T, int NPAD, int MT>
 static int launch_convt_merged(const ConvTParams &p, cudaStream_t st) {
   return g_conv_f16 ? launch_convt_impl<TZ, T, NPAD, MT, 2, true>(p, st) : launch_convt_impl<TZ, T, NPAD, MT, 2, false>(p, st);
 }
+template <int T, int NPAD, int MT>
+static int launch_conv_merged8(const ConvTParams &p, cudaStream_t st) {
+  return g_conv_f16 ? launch_convt_impl<T, T, NPAD, MT, 3, true>(p, st) : launch_convt_impl<T, T, NPAD, MT, 3, false>(p, st);
+}
 
 }  // namespace gb
 
@@ -448,7 +465,7 @@ using namespace gb;
 //   wpack: weights packed by genre_shapehd_b200.ops_conv.pack_convt_weights (layout in the kernel header)
 //   scale, shift [npad]: per-channel affine applied to the accumulator (bias and folded eval-mode BatchNorm),
 //   slope: LeakyReLU slope (1 = none).   out [B*2D][cgo][2H][2W][4]
-// Supported: W in {16, 32}, H % 16 == 0, (cg0 + cg1) even, cg0 even, 4*cgo <= npad, npad in {32, 64}.
+// Supported: W in {16, 32}, H % 16 == 0, cg0 + cg1 even, 4*cgo <= npad, npad in {32, 64}.
 extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
                                              int64_t D, int64_t H, int64_t W, const void *wpack_, int ksize, int npad,
                                              int f16, const float *scale, const float *shift, float slope, float *out,
@@ -460,8 +477,8 @@ extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const v
   GB_REQUIRE(npad == 32 || npad == 64, GENRE_B200_EINVAL, "convt3d: npad %d unsupported (32 or 64)", npad);
   GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "convt3d: input width %lld unsupported (16 or 32)", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt3d: bad extent");
-  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && cg0 % CT_KCG == 0 && cg1 % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
-             "convt3d: channel groups (%d, %d) must be even", cg0, cg1);
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "convt3d: channel groups (%d + %d) must be even in total", cg0, cg1);
   GB_REQUIRE(cgo > 0 && 4 * cgo <= npad, GENRE_B200_EINVAL, "convt3d: %d output channels exceed npad %d", 4 * cgo, npad);
   GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "convt3d: grid too large");
   GB_REQUIRE(aligned16(src0) && aligned16(wpack) && aligned16(out) && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,
@@ -508,8 +525,8 @@ extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, 
   GB_REQUIRE(npad == 80, GENRE_B200_EINVAL, "convt3d_merged: npad %d unsupported (80 = 4 classes x 20 channels)", npad);
   GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "convt3d_merged: input width %lld unsupported (16 or 32)", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt3d_merged: bad extent");
-  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && cg0 % CT_KCG == 0 && cg1 % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
-             "convt3d_merged: channel groups (%d, %d) must be even", cg0, cg1);
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "convt3d_merged: channel groups (%d + %d) must be even in total", cg0, cg1);
   GB_REQUIRE(cgo > 0 && 16 * cgo <= npad, GENRE_B200_EINVAL, "convt3d_merged: %d output channels exceed npad/4", 4 * cgo);
   GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "convt3d_merged: grid too large");
   GB_REQUIRE(aligned16(src0) && aligned16(wpack) && aligned16(out) && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,
@@ -529,6 +546,33 @@ extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, 
   return launch_convt_merged<4, 5, 80, 2>(p, st);
 }
 
+// Conv3d(kernel 8, stride 2, padding 3), few input channels, Cout <= 20, on a 4x space-to-depth input (kernel MODE 3):
+// Unet_3D.enc1 = Conv3d(2 -> 20) on 128^3 (networks/networks.py:151).
+//   src [B*D][cg][H][W][16 B]: D,H,W = input extent / 4, channels ((c*4+rz)*4+ry)*4+rx (genre_b200_ncdhw_to_blocked mode 3)
+//   wpack [3 z-tap][chunk][9 taps][2][npad/8][8][g], npad = 160 columns n = ((qz*2+qy)*2+qx)*20 + co
+//         (ops_conv.pack_conv_k8s2_s4d_weights);  scale, shift [20];  out [B*2D][cgo][2H][2W][4] fp32
+// Supported: W % 16 == 0, H % 16 == 0, cg even.
+extern "C" int genre_b200_conv3d_k8s2_s4d_forward(const void *src_, int cg, int64_t B, int64_t D, int64_t H, int64_t W,
+                                                  const void *wpack_, int npad, int f16, const float *scale,
+                                                  const float *shift, float slope, float *out, int cgo, void *stream) {
+  const float *src = (const float *)src_, *wpack = (const float *)wpack_;
+  g_conv_f16 = f16 != 0;
+  GB_REQUIRE(src && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: null pointer");
+  GB_REQUIRE(npad == 160, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: npad %d unsupported (160 = 8 classes x 20 channels)", npad);
+  GB_REQUIRE(W > 0 && W % 16 == 0 && H > 0 && H % CT_BY == 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: bad extent");
+  GB_REQUIRE(cg > 0 && cg % CT_KCG == 0, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: channel groups must be even");
+  GB_REQUIRE(cgo > 0 && 32 * cgo <= npad, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: too many output channels");
+  GB_REQUIRE(B * D * (H / CT_BY) * (W / 16) < (1ll << 31), GENRE_B200_EINVAL, "conv3d_k8s2_s4d: grid too large");
+  GB_REQUIRE(aligned16(src) && aligned16(wpack) && aligned16(out), GENRE_B200_EALIGN, "conv3d_k8s2_s4d: alignment");
+  ConvTParams p;
+  p.src0 = src; p.src1 = nullptr; p.cg0 = cg; p.cg1 = 0;
+  p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
+  p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
+  p.srcpar_cgs = 0;
+  p.base[0] = p.base[1] = 1;  // input cell = j + 1 - t
+  return launch_conv_merged8<3, 160, 2>(p, as_stream(stream));
+}
+
 // Stride-1 convolution with T taps per dimension on channel-blocked activations (same kernel, one output class):
 //     out[b, z, y, x, n] = act(scale[n] * sum_{tz,ty,tx,c} in[b, z + base - tz, y + base - ty, x + base - tx, c] * Wt[...] + shift[n])
 // A strided Conv3d reaches this form through space-to-depth (genre_shapehd_b200/ops_conv.py): Unet_3D.enc1 =
@@ -546,8 +590,8 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   GB_REQUIRE(npad == 32, GENRE_B200_EINVAL, "conv3d_taps: npad %d unsupported (32)", npad);
   GB_REQUIRE(W == 16 || W == 32 || W == 64, GENRE_B200_EINVAL, "conv3d_taps: width %lld unsupported", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_taps: bad extent");
-  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && cg0 % CT_KCG == 0 && cg1 % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
-             "conv3d_taps: channel groups (%d, %d) must be even", cg0, cg1);
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "conv3d_taps: channel groups (%d + %d) must be even in total", cg0, cg1);
   GB_REQUIRE(cgo > 0 && 4 * cgo <= npad, GENRE_B200_EINVAL, "conv3d_taps: too many output channels");
   GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "conv3d_taps: grid too large");
   GB_REQUIRE(aligned16(src0) && aligned16(wpack) && aligned16(out) && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,

@@ -8,6 +8,7 @@
 //   s2d_blocked   : [B,C,D,H,W] fp32 (even ext) -> [B*D/2][8C/g][H/2][W/2][g], channel = ((c*2+pz)*2+py)*2+px
 //   s2d_sources   : [B,C,D,H,W] fp32 (even ext) -> [B*D/2][8*cpad/g][H/2][W/2][g], the 8 parity sub-volumes one after
 //                   the other along the channel-group axis, each zero-padded from C to cpad channels
+//   s4d_blocked   : [B,C,D,H,W] fp32 (ext % 4)   -> [B*D/4][64C/g][H/4][W/4][g], channel = ((c*4+rz)*4+ry)*4+rx
 //   from_blocked  : [B*D][cg][H][W][4] fp32     -> [B,C,D,H,W] fp32 (drops channel padding)
 #include <cuda_fp16.h>
 
@@ -126,6 +127,36 @@ s2d_sources_kernel(const float *__restrict__ src, void *__restrict__ dst, int C,
   }
 }
 
+// 4x space-to-depth: one thread = one 16-byte unit = 8/G rows of 4 consecutive x of one (c, rz) plane
+template <int G>
+__global__ void __launch_bounds__(LY_THREADS)
+s4d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t units) {
+  const int D4 = D / 4, H4 = H / 4, W4 = W / 4;
+  constexpr int UPP = 16 / G;  // units per (c, rz) plane of 16 (ry, rx) channels
+  const int CGo = C * 4 * UPP;
+  for (size_t u = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; u < units; u += (size_t)gridDim.x * LY_THREADS) {
+    const int x4 = (int)(u % W4);
+    size_t r = u / W4;
+    const int y4 = (int)(r % H4);
+    r /= H4;
+    const int cg = (int)(r % CGo);
+    r /= CGo;  // b * D4 + z'
+    const size_t b = r / D4, z4 = r - b * D4;
+    const int h = cg % UPP, crz = cg / UPP, rz = crz & 3, c = crz >> 2;
+    const float *s = src + (((b * C + c) * D + 4 * z4 + rz) * H + 4 * y4 + h * (G / 4)) * (size_t)W + 4 * x4;
+    float x[G];
+#pragma unroll
+    for (int row = 0; row < G / 4; ++row) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(s + (size_t)row * W));
+      x[row * 4 + 0] = t.x;
+      x[row * 4 + 1] = t.y;
+      x[row * 4 + 2] = t.z;
+      x[row * 4 + 3] = t.w;
+    }
+    store_unit<G>(dst, u, x);
+  }
+}
+
 __global__ void __launch_bounds__(LY_THREADS)
 from_blocked_kernel(const float4 *__restrict__ src, float *__restrict__ dst, int C, int CG, int D, int H, int W,
                     size_t units) {
@@ -156,7 +187,8 @@ static unsigned ly_grid(size_t n) {
 
 using namespace gb;
 
-// mode 0: to_blocked, 1: s2d_blocked, 2: s2d_sources (cpad = padded channels per sub-volume; ignored otherwise).
+// mode 0: to_blocked, 1: s2d_blocked, 2: s2d_sources (cpad = padded channels per sub-volume; ignored otherwise),
+// 3: s4d_blocked.
 // group 4 -> fp32 units, 8 -> fp16 units.  src is contiguous NCDHW fp32.
 extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
                                            int mode, int group, int cpad, void *dst, void *stream) {
@@ -179,6 +211,14 @@ extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t 
     if (group == 4) s2d_blocked_kernel<4><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells);
     else s2d_blocked_kernel<8><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells);
     return check_launch("s2d_blocked kernel");
+  }
+  if (mode == 3) {
+    GB_REQUIRE(D % 4 == 0 && H % 4 == 0 && W % 4 == 0 && aligned16(src), GENRE_B200_EINVAL,
+               "4x space-to-depth: extents must be multiples of 4 and src 16-byte aligned");
+    const size_t units = (size_t)(B * C * 64 / group * (D / 4) * (H / 4) * (W / 4));
+    if (group == 4) s4d_blocked_kernel<4><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
+    else s4d_blocked_kernel<8><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
+    return check_launch("s4d_blocked kernel");
   }
   GB_REQUIRE(mode == 2, GENRE_B200_EINVAL, "to_blocked: unknown mode %d", mode);
   GB_REQUIRE(cpad >= C && cpad % group == 0, GENRE_B200_EINVAL, "s2d_sources: cpad=%d must be >= C and a multiple of %d", cpad, group);

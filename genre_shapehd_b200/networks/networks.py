@@ -198,14 +198,20 @@ class Deconv3d_skip(nn.Module):
         deconv = ConvTranspose3d(ncin, ncout, kernel_size, stride, pad, extra)
         self.net = nn.Sequential(deconv, nn.BatchNorm3d(ncout), nn.LeakyReLU()) if is_activate else deconv
 
-    def forward(self, x, skip_in):
+    def forward(self, x, skip_in, keep_blocked=False):
+        """keep_blocked: the caller promises the result only feeds another Deconv3d_skip (Unet_3D.forward does for
+        dec5 -> dec6), so a custom kernel may leave it in its blocked layout (ops_conv.BlockedActivation)."""
         if not x.is_cuda:
             y = None
         elif isinstance(self.net, nn.Sequential):
-            y = ops_conv.deconv_skip(x, skip_in, self.net[0], self.net[1], self.net[2].negative_slope)
+            y = ops_conv.deconv_skip(x, skip_in, self.net[0], self.net[1], self.net[2].negative_slope, keep_blocked)
         else:
             y = ops_conv.deconv_skip(x, skip_in, self.net)
-        return y if y is not None else self.net(cat((x, skip_in), dim=1))
+        if y is not None:
+            return y
+        if isinstance(x, ops_conv.BlockedActivation):
+            x = x.ncdhw()
+        return self.net(cat((x, skip_in), dim=1))
 
 
 class Unet_3D(nn.Module):
@@ -236,5 +242,5 @@ class Unet_3D(nn.Module):
             b = enc6.size(0)
             x = self.full_conv_block(enc6.view(b, self.nf * 32)).view(b, self.nf * 32, 1, 1, 1)
         for i in range(1, 7):
-            x = getattr(self, "dec%d" % i)(x, skips[6 - i])
+            x = getattr(self, "dec%d" % i)(x, skips[6 - i], keep_blocked=(i == 5))   # dec5's only consumer is dec6
         return x

@@ -94,6 +94,27 @@ def from_blocked(y, batch, channels):
     return out
 
 
+class BlockedActivation:
+    """An activation that exists only in the blocked layout (the output of a custom layer whose sole consumer is the
+    next custom layer, e.g. Unet_3D.dec5 -> dec6).  Quacks like the NCDHW tensor for the dispatch checks; ncdhw()
+    materialises it if a consumer turns out to need the plain layout."""
+    is_cuda, dtype, requires_grad = True, torch.float32, False
+
+    def __init__(self, y, batch, channels):
+        bd, cg, h, w, _ = y.shape
+        self._gb_blocked, self.batch, self.shape = y, batch, torch.Size((batch, channels, bd // batch, h, w))
+        self.device = y.device
+
+    def dim(self):
+        return 5
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def ncdhw(self):
+        return from_blocked(self._gb_blocked, self.batch, self.shape[1])
+
+
 def _blocked_f32(x):
     """fp32 group-of-4 blocked view of an NCDHW tensor: the cached one if x came out of a custom layer"""
     y = getattr(x, "_gb_blocked", None)
@@ -166,11 +187,6 @@ def _cached_pack(module, key, make):
     return hit[1]
 
 
-def _packed(module, npad):
-    g = _group()
-    return _cached_pack(module, ("convt", npad, g), lambda w: pack_convt_weights(w, npad, g))
-
-
 def _convt_supported(shape_bcdhw, module):
     b, c, d, h, w = shape_bcdhw
     k = module.kernel_size[0]
@@ -182,37 +198,32 @@ def _convt_supported(shape_bcdhw, module):
             and c % (2 * _group()) == 0 and module.out_channels <= 64)
 
 
-def convt3d_s2_blocked(src0, src1, batch, module, scale=None, shift=None, slope=1.0):
+def convt3d_s2_blocked(src0, src1, batch, module, bn=None, slope=1.0):
     """Run the kernel on blocked operands (fp32 groups of 4 or fp16 groups of 8, matching PRECISION); returns the
-    blocked fp32 output [B*2D, cgo, 2H, 2W, 4]."""
+    blocked fp32 output [B*2D, cgo, 2H, 2W, 4], or None when `bn` needs batch statistics."""
     bd, cg0, h, w, _ = src0.shape
     cg1 = src1.shape[1] if src1 is not None else 0
     cout = module.out_channels
-    npad = 32 if cout <= 32 else 64
     cgo = (cout + 3) // 4
     dev = src0.device
-    if MERGE_PARITIES and module.kernel_size[0] == 8 and cout <= 20:
-        # the four (y,x) parity classes share one MMA stream: N = 4 x 20 columns (csrc/convt3d.cu MODE 2)
-        g = 8 if src0.dtype == torch.float16 else 4
-        wpack = _cached_pack(module, ("convt_merged", 20, g), lambda wt: pack_convt_merged_weights(wt, 20, g))
-        sc = torch.ones(20, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, 20 - cout), value=1.0)
-        if shift is None:
-            shift = module.bias.detach() if module.bias is not None else torch.zeros(cout, device=dev)
-        sh = torch.nn.functional.pad(shift.float(), (0, 20 - cout))
-        out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=dev, dtype=torch.float32)
-        _lib.call("genre_b200_convt3d_s2_merged_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
-                  cg1, batch, bd // batch, h, w, wpack.data_ptr(), 8, 80, 1 if g == 8 else 0, sc.data_ptr(), sh.data_ptr(),
-                  float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
-        return out
-    wpack = _packed(module, npad)
-    sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
-    if shift is None:
-        shift = module.bias.detach() if module.bias is not None else torch.zeros(cout, device=dev)
-    sh = torch.nn.functional.pad(shift.float(), (0, npad - cout))
+    g = 8 if src0.dtype == torch.float16 else 4
+    merged = MERGE_PARITIES and module.kernel_size[0] == 8 and cout <= 20
+    npad = 20 if merged else 32 if cout <= 32 else 64
+    aff = _affine(module, bn, npad, dev)
+    if aff is None:
+        return None
     out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=dev, dtype=torch.float32)
+    if merged:
+        # the four (y,x) parity classes share one MMA stream: N = 4 x 20 columns (csrc/convt3d.cu MODE 2)
+        wpack = _cached_pack(module, ("convt_merged", 20, g), lambda wt: pack_convt_merged_weights(wt, 20, g))
+        _lib.call("genre_b200_convt3d_s2_merged_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
+                  cg1, batch, bd // batch, h, w, wpack.data_ptr(), 8, 80, 1 if g == 8 else 0, aff[0].data_ptr(),
+                  aff[1].data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
+        return out
+    wpack = _cached_pack(module, ("convt", npad, g), lambda wt: pack_convt_weights(wt, npad, g))
     _lib.call("genre_b200_convt3d_s2_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None, cg1,
-              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, 1 if src0.dtype == torch.float16 else 0,
-              sc.data_ptr(), sh.data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
+              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, 1 if g == 8 else 0,
+              aff[0].data_ptr(), aff[1].data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
     return out
 
 
@@ -241,6 +252,44 @@ def space_to_depth_blocked(x, group=4, dtype=None):
     else:           # s == 2: j = pz, e = (py,px)
         v = t.permute(0, 2, 1, 3, 4, 6, 5, 7)            # b z' c pz y' x' py px
     return _permuted_copy(v, dtype).view(b * (d // 2), c * s, h // 2, w // 2, group)
+
+
+def space_to_depth4_blocked(x, group=4, dtype=None):
+    """NCDHW [B,C,D,H,W] (extents % 4 == 0) -> blocked [B*D/4, 64C/group, H/4, W/4, group], channel index
+    ((c*4 + rz)*4 + ry)*4 + rx for input position (4z'+rz, 4y'+ry, 4x'+rx)."""
+    b, c, d, h, w = x.shape
+    out_shape = (b * (d // 4), c * 64 // group, h // 4, w // 4, group)
+    if _on_device(x, group, dtype):
+        out = torch.empty(out_shape, device=x.device, dtype=dtype or x.dtype)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 3, group, 0, out.data_ptr(), _lib.stream_ptr(x))
+        return out
+    t = x.reshape(b, c, d // 4, 4, h // 4, 4, w // 4, 4).permute(0, 2, 1, 3, 5, 7, 4, 6)   # b z' c rz ry rx y' x'
+    t = t.reshape(b * (d // 4), c * 64 // group, group, h // 4, w // 4).permute(0, 1, 3, 4, 2)
+    return _permuted_copy(t, dtype)
+
+
+def pack_conv_k8s2_s4d_weights(weight, cpad, group=4):
+    """Conv3d weight [Cout, Cin, 8, 8, 8] (stride 2, padding 3) -> the 3-tap stride-1 convolution over the 64*Cin
+    4x-space-to-depth channels whose N = 8*cpad columns are the 8 output classes q of the 2x finer output grid:
+    [3 z-tap][chunk][9 taps][2][N/8][8][g].  Per dimension: output 2j+q reads input 4j + 2q - 3 + k; coarse cell
+    j + 1 - t, sub-position r  =>  k = 7 - 4t + r - 2q (zero weight when outside [0, 8))."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    g, n = group, 8 * cpad
+    q = torch.arange(2).view(2, 1, 1)
+    t = torch.arange(3).view(1, 3, 1)
+    r = torch.arange(4).view(1, 1, 4)
+    k = 7 - 4 * t + r - 2 * q                                             # [q, t, r]
+    valid = ((k >= 0) & (k < 8)).to(weight.device)
+    kc = k.clamp(0, 7).to(weight.device)
+    kz, vz = kc.view(2, 3, 4, 1, 1, 1, 1, 1, 1), valid.view(2, 3, 4, 1, 1, 1, 1, 1, 1)
+    ky, vy = kc.view(1, 1, 1, 2, 3, 4, 1, 1, 1), valid.view(1, 1, 1, 2, 3, 4, 1, 1, 1)
+    kx, vx = kc.view(1, 1, 1, 1, 1, 1, 2, 3, 4), valid.view(1, 1, 1, 1, 1, 1, 2, 3, 4)
+    full = weight[:, :, kz, ky, kx] * (vz & vy & vx).to(weight.dtype)      # [co, c, qz,tz,rz, qy,ty,ry, qx,tx,rx]
+    weq = full.permute(1, 4, 7, 10, 2, 5, 8, 0, 3, 6, 9)                  # c rz ry rx | qz qy qx co | tz ty tx
+    weq = torch.nn.functional.pad(weq, (0, 0, 0, 0, 0, 0, 0, cpad - cout)).reshape(cin * 64, n, 3, 3, 3)
+    sub = weq.reshape(cin * 64 // (2 * g), 2, g, n // 8, 8, 3, 3, 3)      # (kc, kk, e, ng, r, tz, ty, tx)
+    out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                # (tz, kc, ty, tx, kk, ng, r, e)
+    return out.half() if g == 8 else out
 
 
 def pack_conv_k8s2_weights(weight, npad, group=4):
@@ -327,21 +376,35 @@ def _conv_k4s2_supported(x, m):
             and all(v % 2 == 0 for v in x.shape[2:]) and x.shape[4] // 2 in (16, 32) and (x.shape[3] // 2) % 16 == 0)
 
 
+def _versions(*tensors):
+    return tuple((t._version, t.data_ptr()) if t is not None else None for t in tensors)
+
+
 def _affine(m, bn, npad, dev):
-    """(scale, shift) [npad] of the epilogue: bias, and eval-mode BatchNorm folded in; None if bn needs batch statistics"""
+    """(scale, shift) [npad] of the epilogue: bias, and eval-mode BatchNorm folded in; None if bn needs batch statistics.
+    Cached on the conv module until one of the source tensors is modified in place or replaced."""
     cout = m.out_channels
+    if bn is not None and (bn.training or not bn.track_running_stats):
+        return None
+    ver = (_versions(m.bias, *((bn.running_mean, bn.running_var, bn.weight, bn.bias) if bn is not None else ())),
+           bn.eps if bn is not None else None, str(dev))
+    cache = m.__dict__.setdefault("_gb_affine", {})
+    hit = cache.get(npad)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
     scale = shift = None
-    if bn is not None:
-        if bn.training or not bn.track_running_stats:
-            return None
-        inv = torch.rsqrt(bn.running_var + bn.eps)
-        scale = inv * (bn.weight if bn.weight is not None else 1.0)
-        bias = m.bias.detach() if m.bias is not None else torch.zeros_like(bn.running_mean)
-        shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
-    sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
-    if shift is None:
-        shift = m.bias.detach() if m.bias is not None else torch.zeros(cout, device=dev)
-    return sc, torch.nn.functional.pad(shift.float(), (0, npad - cout))
+    with torch.no_grad():
+        if bn is not None:
+            inv = torch.rsqrt(bn.running_var + bn.eps)
+            scale = inv * (bn.weight if bn.weight is not None else 1.0)
+            bias = m.bias.detach() if m.bias is not None else torch.zeros_like(bn.running_mean)
+            shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
+        sc = torch.ones(npad, device=dev) if scale is None else torch.nn.functional.pad(scale.float(), (0, npad - cout), value=1.0)
+        if shift is None:
+            shift = m.bias.detach() if m.bias is not None else torch.zeros(cout, device=dev)
+        out = (sc.contiguous(), torch.nn.functional.pad(shift.float(), (0, npad - cout)).contiguous())
+    cache[npad] = (ver, out)
+    return out
 
 
 def _conv_k4s2(x, m, bn, slope):
@@ -374,6 +437,21 @@ def conv3d(x, m, bn=None, slope=None):
         return _conv_k4s2(x, m, bn, slope)
     if not _conv_k8s2_supported(x, m):
         return None
+    if MERGE_PARITIES and m.out_channels <= 20 and all(v % 64 == 0 for v in x.shape[3:]) and x.shape[2] % 4 == 0:
+        # 4x space-to-depth: 3 taps over 64*Cin channels, the 8 output classes of the 2x finer grid merged along N
+        aff = _affine(m, bn, 20, x.device)
+        if aff is None:
+            return None
+        g, b, cout = _group(), x.shape[0], m.out_channels
+        wpack = _cached_pack(m, ("k8s2_s4d", 20, g), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g))
+        xb = space_to_depth4_blocked(x, g, torch.float16 if _f16() else None)
+        bd, cg, h, w, _ = xb.shape
+        cgo = (cout + 3) // 4
+        out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=x.device, dtype=torch.float32)
+        _lib.call("genre_b200_conv3d_k8s2_s4d_forward", xb.data_ptr(), cg, b, bd // b, h, w, wpack.data_ptr(), 160,
+                  1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
+                  out.data_ptr(), cgo, _lib.stream_ptr(x))
+        return from_blocked(out, b, cout)
     cout, npad = m.out_channels, 32
     aff = _affine(m, bn, npad, x.device)
     if aff is None:
@@ -411,7 +489,13 @@ def convt_c1(src0, src1, batch, m):
     d = bd // batch
     out = torch.empty((batch, 1, 2 * d, 2 * h, 2 * w), device=src0.device, dtype=torch.float32)
     wt = m.weight.detach().reshape(m.in_channels, 64).contiguous()
-    bias = float(m.bias.detach()) if m.bias is not None else 0.0
+    bias = 0.0
+    if m.bias is not None:   # the C ABI takes the scalar by value: read it back once per parameter version, not per call
+        ver = _versions(m.bias)
+        hit = m.__dict__.get("_gb_bias")
+        if hit is None or hit[0] != ver:
+            hit = m.__dict__["_gb_bias"] = (ver, float(m.bias.detach()))
+        bias = hit[1]
     _lib.call("genre_b200_convt_c1_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
               src1.shape[1] if src1 is not None else 0, batch, d, h, w, wt.data_ptr(), bias, 0, out.data_ptr(),
               _lib.stream_ptr(src0))
@@ -429,7 +513,7 @@ def conv_transpose3d(x, m):
     return from_blocked(y, x.shape[0], m.out_channels)
 
 
-def deconv_skip(x, skip, conv, bn=None, slope=None):
+def deconv_skip(x, skip, conv, bn=None, slope=None, keep_blocked=False):
     """cat(x, skip) -> ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> LeakyReLU(slope)] with the
     concatenation walked as two K ranges instead of being materialised.  None if not covered."""
     if (bn is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
@@ -437,24 +521,19 @@ def deconv_skip(x, skip, conv, bn=None, slope=None):
             and _convt_c1_supported(x.shape[1] + skip.shape[1], x.shape[2:], conv, (x, skip))
             and _no_autograd(x, skip, conv.weight, conv.bias)):
         return convt_c1(_blocked_f32(x), _blocked_f32(skip), x.shape[0], conv)
+    if isinstance(x, BlockedActivation):
+        x = x.ncdhw()
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
             and x.shape[1] % _group() == 0 and skip.shape[1] % _group() == 0
             and _convt_supported((x.shape[0], x.shape[1] + skip.shape[1]) + tuple(x.shape[2:]), conv)
             and _no_autograd(x, skip, conv.weight, conv.bias)):
         return None
-    scale = shift = None
-    if bn is not None:
-        if bn.training or not bn.track_running_stats:
-            return None  # batch statistics need the un-normalised output first
-        inv = torch.rsqrt(bn.running_var + bn.eps)
-        scale = inv * (bn.weight if bn.weight is not None else 1.0)
-        bias = conv.bias.detach() if conv.bias is not None else torch.zeros_like(bn.running_mean)
-        shift = (bias - bn.running_mean) * scale + (bn.bias if bn.bias is not None else 0.0)
-    g2 = 2 * _group()
-    if x.shape[1] % g2 == 0 and skip.shape[1] % g2 == 0:
-        a, bsrc = _to_operand(x), _to_operand(skip)          # the concatenation stays two K ranges
-    else:
-        # a K chunk (2 channel groups) may not straddle the two tensors: join them in the blocked domain instead
-        a, bsrc = torch.cat((_to_operand(x), _to_operand(skip)), dim=1), None
-    y = convt3d_s2_blocked(a, bsrc, x.shape[0], conv, scale, shift, 1.0 if slope is None else slope)
+    if bn is not None and (bn.training or not bn.track_running_stats):
+        return None  # batch statistics need the un-normalised output first
+    # the concatenation stays two K ranges (a K chunk of 2 channel groups may straddle them: the halo producer picks the
+    # source per channel group)
+    a, bsrc = _to_operand(x), _to_operand(skip)
+    y = convt3d_s2_blocked(a, bsrc, x.shape[0], conv, bn, 1.0 if slope is None else slope)
+    if keep_blocked:
+        return BlockedActivation(y, x.shape[0], conv.out_channels)
     return from_blocked(y, x.shape[0], conv.out_channels)

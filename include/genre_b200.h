@@ -179,7 +179,7 @@ int genre_b200_voxelize_stage_splat(int64_t n_maps, int64_t pixels_per_map, int 
  *   wpack   weights packed per (parity, z-tap, 8-channel chunk) stage: see genre_shapehd_b200/ops_conv.py
  *   scale, shift [npad]   y = act(acc * scale + shift): bias and folded eval-mode BatchNorm3d
  *   slope   LeakyReLU slope (1 = none);   out [B*2D][cgo][2H][2W][4]
- * Supported: W in {16,32}, H % 16 == 0, cg0, cg1 even, 4*cgo <= npad, npad in {32,64}.
+ * Supported: W in {16,32}, H % 16 == 0, cg0 + cg1 even, 4*cgo <= npad, npad in {32,64}.
  * ------------------------------------------------------------------------------------------- */
 int genre_b200_convt3d_s2_forward(const void *src0, int cg0, const void *src1, int cg1,
                                   int64_t B, int64_t D, int64_t H, int64_t W,
@@ -227,10 +227,20 @@ int genre_b200_convt3d_s2_merged_forward(const void *src0, int cg0, const void *
                                          const float *scale, const float *shift, float slope,
                                          float *out, int cgo, void *stream);
 
+/* Conv3d(k 8, s 2, p 3), Cout <= 20, as a 3-tap stride-1 convolution over the 4x space-to-depth input whose N = 160
+ * columns are the 8 output classes of the 2x finer output grid: Unet_3D.enc1 = Conv3d(2 -> 20) on 128^3
+ * (networks/networks.py:151).  src [B*D][cg][H][W][16 B] with D,H,W = input extent / 4 (genre_b200_ncdhw_to_blocked
+ * mode 3); wpack [3][chunk][9][2][20][8][g]; scale, shift [20]; out [B*2D][cgo][2H][2W][4] fp32.  W,H % 16 == 0. */
+int genre_b200_conv3d_k8s2_s4d_forward(const void *src, int cg, int64_t B, int64_t D, int64_t H, int64_t W,
+                                       const void *wpack, int npad, int f16,
+                                       const float *scale, const float *shift, float slope,
+                                       float *out, int cgo, void *stream);
+
 /* Layout boundary of the convolution kernels: contiguous NCDHW fp32 (what networks/networks.py's modules exchange,
  * e.g. Unet_3D.forward networks.py:170-190) <-> channel-blocked [B*D][C/g][H][W][g] (16 bytes per unit).
  *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1);
- *   mode 2: the 8 parity sub-volumes one after the other, each padded to cpad channels (Conv3d k4 s2).
+ *   mode 2: the 8 parity sub-volumes one after the other, each padded to cpad channels (Conv3d k4 s2);
+ *   mode 3: 4x space-to-depth, channel = ((c*4+rz)*4+ry)*4+rx (Conv3d k8 s2 as a 3-tap convolution, Unet_3D.enc1).
  *   group 4: fp32 units, group 8: fp16 units (cast on the way).  One pass, 16-byte stores. */
 int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
                                 int mode, int group, int cpad, void *dst, void *stream);

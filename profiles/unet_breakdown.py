@@ -23,6 +23,11 @@ def hook_post(name):
     return f
 for n in ["enc%d" % i for i in range(1, 7)] + ["full_conv_block"] + ["dec%d" % i for i in range(1, 7)]:
     mod = getattr(net, n); mod.register_forward_pre_hook(hook_pre(n)); mod.register_forward_hook(hook_post(n))
+if os.environ.get("NCU"):   # kernel list of ONE warm forward: run under `ncu --profile-from-start off`
+    with torch.no_grad():
+        for _ in range(2): net(x)
+        torch.cuda.synchronize(); torch.cuda.profiler.start(); net(x); torch.cuda.synchronize(); torch.cuda.profiler.stop()
+    sys.exit(0)
 res = {}
 for mode, enabled, tf32 in (("custom", True, True), ("cudnn_tf32", False, True)):
     ops_conv.ENABLED = enabled; torch.backends.cudnn.allow_tf32 = tf32

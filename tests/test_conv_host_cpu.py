@@ -86,6 +86,26 @@ def test_pack_conv_k8s2_weights_space_to_depth():
     assert torch.allclose(y, ref, atol=1e-5)
 
 
+def test_pack_conv_k8s2_s4d_weights_merged_classes():
+    """4x space-to-depth + 3 taps + the 8 output classes along N (csrc/convt3d.cu MODE 3)"""
+    torch.manual_seed(6)
+    cin, cout, cpad = 2, 5, 8
+    wt = torch.randn(cout, cin, 8, 8, 8)
+    x = torch.randn(2, cin, 8, 12, 16)
+    ref = F.conv3d(x.double(), wt.double(), stride=2, padding=3)
+    wp = ops_conv.pack_conv_k8s2_s4d_weights(wt, cpad, 4)
+    assert wp.shape[:4] == (3, cin * 64 // 8, 3, 3) and wp.shape[5] * 8 == 8 * cpad
+    xb = ops_conv.space_to_depth4_blocked(x, 4)
+    y = _taps_gemm(xb, 2, wp, 1, 1, 1)                                              # [B, D/4, H/4, W/4, 8*cpad]
+    out = torch.zeros_like(ref)
+    for qz in (0, 1):
+        for qy in (0, 1):
+            for qx in (0, 1):
+                c0 = ((qz * 2 + qy) * 2 + qx) * cpad
+                out[:, :, qz::2, qy::2, qx::2] = y[..., c0:c0 + cout].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
 def test_pack_conv_k4s2_weights_parity_sources():
     torch.manual_seed(4)
     cin, cout, cpad, npad, g = 5, 6, 8, 8, 4

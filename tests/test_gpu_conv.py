@@ -85,6 +85,9 @@ def test_layout_kernels_match_torch_permutes(group, dtype):
     x2 = torch.randn(3, 2, 4, 6, 8, device=DEV)
     assert torch.equal(ops_conv.space_to_depth_blocked(x2, group, dtype).cpu(),
                        ops_conv.space_to_depth_blocked(x2.cpu(), group, dtype))
+    x4 = torch.randn(2, 3, 8, 4, 12, device=DEV)
+    assert torch.equal(ops_conv.space_to_depth4_blocked(x4, group, dtype).cpu(),
+                       ops_conv.space_to_depth4_blocked(x4.cpu(), group, dtype))
     x3 = torch.randn(2, 5, 4, 6, 8, device=DEV)           # 5 channels padded to 8 / 16 per sub-volume
     for cpad in (8, 16):
         assert torch.equal(ops_conv.space_to_depth_sources(x3, cpad, group, dtype).cpu(),
@@ -120,7 +123,8 @@ def test_autograd_and_unsupported_shapes_fall_back():
         assert ops_conv.conv_transpose3d(torch.randn(1, 16, 2, 8, 8, device=DEV), m) is None   # W=8 not covered
 
 
-@pytest.mark.parametrize("cin,cout,b,d,h,w", [(2, 20, 1, 4, 32, 32), (2, 20, 2, 8, 64, 64), (4, 12, 1, 6, 32, 128)])
+@pytest.mark.parametrize("cin,cout,b,d,h,w", [(2, 20, 1, 4, 32, 32), (2, 20, 2, 8, 64, 64), (4, 12, 1, 6, 32, 128),
+                                                 (2, 20, 1, 4, 64, 128), (4, 7, 1, 8, 128, 64)])
 def test_conv3d_k8s2_via_space_to_depth_vs_torch(cin, cout, b, d, h, w):
     torch.manual_seed(cin * 100 + cout + w)
     m = nets.Conv3d(cin, cout, 8, 2, 3).to(DEV)
