@@ -36,6 +36,31 @@ class ConvTranspose3d(nn.ConvTranspose3d):
         return y if y is not None else super().forward(x, output_size)
 
 
+class FusedSequential(nn.Sequential):
+    """nn.Sequential (same state_dict keys) whose CUDA forward hands conv [-> BatchNorm3d] -> ReLU/LeakyReLU runs to
+    ops_conv.fused_block: one kernel with the eval-mode normalisation and the activation in its epilogue.  Anything
+    not covered (training-mode BN, autograd, unsupported shapes, CPU) runs module by module like nn.Sequential."""
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, (Conv3d, ConvTranspose3d)) and x.is_cuda:
+                j = i + 1
+                bn = mods[j] if j < len(mods) and isinstance(mods[j], nn.BatchNorm3d) else None
+                j += bn is not None
+                act = mods[j] if j < len(mods) and isinstance(mods[j], (nn.ReLU, nn.LeakyReLU)) else None
+                if act is not None:
+                    y = ops_conv.fused_block(x, m, bn, act)
+                    if y is not None:
+                        x, i = y, j + 1
+                        continue
+            x = m(x)
+            i += 1
+        return x
+
+
 # ---- layer helpers (names and arguments of networks.py:225-284) ------------------------------------------------
 def relu():
     return nn.ReLU(inplace=True)
@@ -124,7 +149,7 @@ def _deconv_stack(n_in, widths, bias, last_sigmoid=False, pad_slots=()):
             layers += [batchnorm3d(cout), relu()]
     if last_sigmoid:
         layers.append(nn.Sigmoid())
-    return nn.Sequential(*layers)
+    return FusedSequential(*layers)
 
 
 class VoxelDecoder(nn.Module):
@@ -171,7 +196,7 @@ class VoxelDiscriminator(nn.Module):
             # the reference creates the extra nf->nf stage last and splices it in after the first stage
             # (networks.py:128-139); same creation order => same parameters under the same seed
             layers[2:2] = [conv3d_half(nf, nf, bias), relu_leaky()]
-        self.main = nn.Sequential(*layers)
+        self.main = FusedSequential(*layers)
 
     def forward(self, x):
         y = self.main(x)

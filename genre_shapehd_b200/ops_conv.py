@@ -19,21 +19,22 @@ import torch
 from . import _lib
 
 ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
-# Dispatch policy.  Every kernel is correct on every layer it supports (tests force all of them on), but around a
-# kernel sit two layout conversions (NCDHW <-> channel-blocked); measured end to end on a B200 (profiles/
-# r01_conv_summary.md) the custom path wins where cuDNN is far off its own pace and is break-even or slower on the
-# "ordinary" k=4 layers, so by default only the winning cases are routed here:
-#   convt_k8   ConvTranspose3d k=8 s=2 (Unet_3D.dec5: 7.2 -> 3.5 ms)                                       ON
-#   conv_k8s2  Conv3d k=8 s=2 on few input channels (Unet_3D.enc1: 16.6 -> 2.2 ms)                         ON
-#   convt_c1   ConvTranspose3d k=4 -> 1 channel when the inputs are already blocked (Unet_3D.dec6: 2.1 -> 1.4) ON
-#   convt_k4   ConvTranspose3d k=4 s=2 (dec4, VoxelDecoder/Generator stages: kernel faster, conversions eat it)  off
-#   conv_k4s2  Conv3d k=4 s=2 (discriminator, enc2/enc3: slower end to end)                                  off
-#   convt_c1_convert   the 1-channel layer when its input must first be converted (VoxelDecoder/Generator)   off
-# GENRE_B200_CONV_POLICY="all" (or a comma list) overrides.
-_default_policy = {"convt_k8", "conv_k8s2", "convt_c1"}
-_all_policy = _default_policy | {"convt_k4", "conv_k4s2", "convt_c1_convert"}
+# Dispatch policy.  Every kernel is correct on every layer it supports; which layers are ROUTED to it is decided by
+# end-to-end measurements on a B200 (kernel + the NCDHW <-> channel-blocked conversions of csrc/layout.cu around it;
+# profiles/r01_conv_summary.md), B = 16, against cuDNN with TF32 allowed:
+#   convt_k8   ConvTranspose3d k=8 s=2 (Unet_3D.dec5: 7.2 -> 1.35 ms)
+#   conv_k8s2  Conv3d k=8 s=2 on few input channels (Unet_3D.enc1: 16.6 -> 0.8 ms)
+#   convt_c1   ConvTranspose3d k=4 -> 1 channel on already-blocked inputs (Unet_3D.dec6: 2.1 -> 1.3 ms)
+#   convt_k4   ConvTranspose3d k=4 s=2 (dec4 0.30 -> 0.23, VoxelDecoder/Generator stages 1.26 -> 1.01, 1.87 -> 1.46 ms)
+#   conv_k4s2  Conv3d k=4 s=2 (discriminator 1.18 -> 0.86 ms per layer, Unet_3D.enc2/enc3)
+#   convt_c1_convert   the 1-channel layer when its input must first be converted; FP32-pipe kernel, so only up to
+#                      C1_MAX_CIN input channels (VoxelDecoder's 32 -> 1 wins, VoxelGenerator's 64 -> 1 does not)
+# GENRE_B200_CONV_POLICY = comma list restricts the set ("all" = everything, the default).
+_all_policy = {"convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert"}
+_default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
-POLICY = set(_all_policy) if _env == "all" else (set(x for x in _env.split(",") if x) or set(_default_policy))
+POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
+C1_MAX_CIN = 48
 K4S2_MIN_CIN = 8
 # Operand type of the tensor-core kernels: "f16" (default) = fp16 operands, fp32 accumulation: the same 10-bit
 # mantissa as TF32 with half the operand bytes (the kernels are bound by shared-memory operand bandwidth, so ~2x
@@ -90,7 +91,7 @@ def from_blocked(y, batch, channels):
         _lib.call("genre_b200_blocked_to_ncdhw", y.data_ptr(), cg, batch, channels, d, h, w, out.data_ptr(), _lib.stream_ptr(y))
     else:
         out = y.view(batch, d, cg, h, w, 4).permute(0, 2, 5, 1, 3, 4).reshape(batch, cg * 4, d, h, w)[:, :channels]
-    out._gb_blocked = y
+    out._gb_blocked = (y, out._version)   # valid until `out` is modified in place (e.g. an inplace ReLU)
     return out
 
 
@@ -115,9 +116,19 @@ class BlockedActivation:
         return from_blocked(self._gb_blocked, self.batch, self.shape[1])
 
 
+def _cached_blocked(x):
+    """the blocked twin a custom layer attached to its NCDHW result, unless that result was since modified in place"""
+    if isinstance(x, BlockedActivation):
+        return x._gb_blocked
+    hit = getattr(x, "_gb_blocked", None)
+    if hit is None or hit[1] != x._version:
+        return None
+    return hit[0]
+
+
 def _blocked_f32(x):
     """fp32 group-of-4 blocked view of an NCDHW tensor: the cached one if x came out of a custom layer"""
-    y = getattr(x, "_gb_blocked", None)
+    y = _cached_blocked(x)
     if y is not None and y.shape[1] * 4 >= x.shape[1] and y.shape[0] == x.shape[0] * x.shape[2] \
             and (y.shape[1] - 1) * 4 < x.shape[1] + 4 and x.shape[1] % 4 == 0:
         return y
@@ -372,7 +383,6 @@ def _conv_k4s2_supported(x, m):
     return ("conv_k4s2" in POLICY and ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and tuple(m.kernel_size) == (4, 4, 4)
             and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1) and tuple(m.dilation) == (1, 1, 1)
             and m.groups == 1 and m.out_channels <= 128 and x.shape[1] >= K4S2_MIN_CIN and m.padding_mode == "zeros"
-            and x.shape[1] % (2 * _group()) == 0
             and all(v % 2 == 0 for v in x.shape[2:]) and x.shape[4] // 2 in (16, 32) and (x.shape[3] // 2) % 16 == 0)
 
 
@@ -470,7 +480,7 @@ def conv3d(x, m, bn=None, slope=None):
 
 
 def _has_blocked(x):
-    return getattr(x, "_gb_blocked", None) is not None
+    return _cached_blocked(x) is not None
 
 
 def _convt_c1_supported(cin, shape_dhw, m, inputs=()):
@@ -480,7 +490,7 @@ def _convt_c1_supported(cin, shape_dhw, m, inputs=()):
         return False
     return (ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1)
             and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1
-            and m.out_channels == 1 and cin % 4 == 0 and cin <= 192 and shape_dhw[2] % 4 == 0)
+            and m.out_channels == 1 and cin % 4 == 0 and cin <= C1_MAX_CIN and shape_dhw[2] % 4 == 0)
 
 
 def convt_c1(src0, src1, batch, m):
@@ -502,15 +512,26 @@ def convt_c1(src0, src1, batch, m):
     return out
 
 
-def conv_transpose3d(x, m):
-    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_c1_supported(x.shape[1], x.shape[2:], m, (x,))
-            and _no_autograd(x, m.weight, m.bias)):
+def conv_transpose3d(x, m, bn=None, slope=None):
+    """ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> ReLU / LeakyReLU(slope)]; None if not covered
+    (the caller then runs the plain modules)."""
+    if (bn is None and slope is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+            and _convt_c1_supported(x.shape[1], x.shape[2:], m, (x,)) and _no_autograd(x, m.weight, m.bias)):
         return convt_c1(_blocked_f32(x), None, x.shape[0], m)
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and _convt_supported(x.shape, m)
             and _no_autograd(x, m.weight, m.bias)):
         return None
-    y = convt3d_s2_blocked(_to_operand(x), None, x.shape[0], m)
-    return from_blocked(y, x.shape[0], m.out_channels)
+    y = convt3d_s2_blocked(_to_operand(x), None, x.shape[0], m, bn, 1.0 if slope is None else slope)
+    return None if y is None else from_blocked(y, x.shape[0], m.out_channels)
+
+
+def fused_block(x, conv, bn, act):
+    """conv [-> BatchNorm3d] -> ReLU/LeakyReLU as ONE kernel launch when the conv has a custom kernel: the normalisation
+    and activation passes over the activation (0.9 ms of VoxelGenerator's 64^3 stage at B=16) disappear into the epilogue."""
+    slope = 0.0 if isinstance(act, torch.nn.ReLU) else float(act.negative_slope)
+    if isinstance(conv, torch.nn.ConvTranspose3d):
+        return conv_transpose3d(x, conv, bn, slope)
+    return conv3d(x, conv, bn, slope)
 
 
 def deconv_skip(x, skip, conv, bn=None, slope=None, keep_blocked=False):
