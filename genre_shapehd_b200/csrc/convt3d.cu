@@ -41,6 +41,7 @@ struct ConvTParams {
   int cgo;                   // output channel groups
   int base[2];               // input index = j + base[par] - t
   int xtiles;                // the CTA tile is 8*MT positions wide; W = xtiles * 8 * MT (set by the launcher)
+  int act_sigmoid = 0;       // MODE 4: apply a sigmoid after the bias
   int srcpar_cgs;            // 0, or: the K range is 8 parity sub-volumes of srcpar_cgs channel groups each (strided
                              // Conv3d k=4 s=2 p=1 after space-to-depth); sub-volume s = (pz,py,px) uses base 1 - p per dim
 };
@@ -154,6 +155,18 @@ __device__ __forceinline__ void tmem_ld4x2(uint32_t taddr0, uint32_t taddr1, flo
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------
 // T: taps per dimension of a parity class (K/2: 2 for k=4, 4 for k=8); NPAD: padded Cout (32 or 64); MT = W/8.
 template <int T, int NPAD, int MT>
@@ -186,11 +199,14 @@ struct ConvTCfg {
 //         (n = ((qz*2+qy)*2+qx)*Cout + co, written to output position 2*j + q): a strided Conv3d(k 8, s 2, p 3) on
 //         a 4x space-to-depth input (Unet_3D.enc1: 2 -> 128 channels, 3 taps, N = 8 x 20) - the same "few wide
 //         MMAs instead of many narrow ones" trade as MODE 2, for a forward convolution.
+// MODE 4: ConvTranspose3d(k 4, s 2, p 1) to ONE output channel (the last layer of every decoder): MODE 3's geometry with
+//         N = 16 columns of which 8 are the output classes; the epilogue adds the bias (shift[0]), optionally applies
+//         the sigmoid, and writes the NCDHW fp32 volume directly.
 template <int TZ, int T, int NPAD, int MT, int MODE, bool F16>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 convt3d_s2_kernel(const ConvTParams p) {
   using Cfg = ConvTCfg<T, NPAD, MT>;
-  constexpr bool PAR = MODE == 0, MERGE = MODE == 2, MERGE8 = MODE == 3;
+  constexpr bool PAR = MODE == 0, MERGE = MODE == 2, MERGE8 = MODE == 3, C1 = MODE == 4;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *stages = smem;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -310,10 +326,29 @@ convt3d_s2_kernel(const ConvTParams p) {
     tc_fence_after();
     const int m = warp * 32 + lane;  // accumulator row = TMEM lane
     const int yy = m >> 3, xx = m & 7;
-    constexpr bool UP = PAR || MERGE || MERGE8;
+    constexpr bool UP = PAR || MERGE || MERGE8 || C1;
     const int Ho = UP ? 2 * p.H : p.H, Wo = UP ? 2 * p.W : p.W, Do = UP ? 2 * p.D : p.D;
     const int oz_plain = UP ? 2 * zj + pz : zj, oy = PAR ? 2 * (y0 + yy) + py : y0 + yy;
-    if constexpr (MERGE || MERGE8) {
+    if constexpr (C1) {
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const float bias = __ldg(p.shift);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        float v[8];
+        tmem_ld8(trow + (uint32_t)(mt * NPAD), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] += bias;
+          if (p.act_sigmoid) v[i] = 1.0f / (1.0f + __expf(-v[i]));
+        }
+        const int oxb = 2 * (x0 + 8 * mt + xx);
+#pragma unroll
+        for (int qzy = 0; qzy < 4; ++qzy) {
+          float *dst = p.out + (((size_t)b * Do + 2 * zj + (qzy >> 1)) * Ho + 2 * (y0 + yy) + (qzy & 1)) * (size_t)Wo + oxb;
+          *reinterpret_cast<float2 *>(dst) = make_float2(v[qzy * 2], v[qzy * 2 + 1]);
+        }
+      }
+    } else if constexpr (MERGE || MERGE8) {
       constexpr int NZ = MERGE8 ? 2 : 1;      // z classes held by this CTA's accumulators
       constexpr int CP = NPAD / (4 * NZ);     // output channels per class
       static_assert(CP % 4 == 0, "merged classes must be whole channel groups");
@@ -451,6 +486,10 @@ template <int TZ, int T, int NPAD, int MT>
 static int launch_convt_merged(const ConvTParams &p, cudaStream_t st) {
   return g_conv_f16 ? launch_convt_impl<TZ, T, NPAD, MT, 2, true>(p, st) : launch_convt_impl<TZ, T, NPAD, MT, 2, false>(p, st);
 }
+template <int MT>
+static int launch_convt_c1(const ConvTParams &p, cudaStream_t st) {
+  return g_conv_f16 ? launch_convt_impl<3, 3, 16, MT, 4, true>(p, st) : launch_convt_impl<3, 3, 16, MT, 4, false>(p, st);
+}
 template <int T, int NPAD, int MT>
 static int launch_conv_merged8(const ConvTParams &p, cudaStream_t st) {
   return g_conv_f16 ? launch_convt_impl<T, T, NPAD, MT, 3, true>(p, st) : launch_convt_impl<T, T, NPAD, MT, 3, false>(p, st);
@@ -571,6 +610,38 @@ extern "C" int genre_b200_conv3d_k8s2_s4d_forward(const void *src_, int cg, int6
   p.srcpar_cgs = 0;
   p.base[0] = p.base[1] = 1;  // input cell = j + 1 - t
   return launch_conv_merged8<3, 160, 2>(p, as_stream(stream));
+}
+
+// ConvTranspose3d(Cin -> 1, k 4, s 2, p 1) on the tensor cores (kernel MODE 4): the last layer of every decoder
+// (Unet_3D.dec6 networks/networks.py:167-168, VoxelDecoder main.17 :57, VoxelGenerator :98).  3 union taps per dimension,
+// the 8 output classes as N columns.
+//   src0/src1 blocked operands [B*D][cg][H][W][16 B] (two halves of a skip concatenation; src1 may be NULL)
+//   wpack [3][chunk][9][2][2][8][g] (ops_conv.pack_convt_c1_tc_weights), bias, act_sigmoid;  out [B][2D][2H][2W] fp32
+// Supported: W in {16, 32, 64}, H % 16 == 0, cg0 + cg1 even.
+extern "C" int genre_b200_convt_c1_tc_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B, int64_t D,
+                                              int64_t H, int64_t W, const void *wpack_, int f16, const float *bias,
+                                              int act_sigmoid, float *out, void *stream) {
+  const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
+  g_conv_f16 = f16 != 0;
+  GB_REQUIRE(src0 && wpack && bias && out, GENRE_B200_EINVAL, "convt_c1_tc: null pointer");
+  GB_REQUIRE(W == 16 || W == 32 || W == 64, GENRE_B200_EINVAL, "convt_c1_tc: input width %lld unsupported", (long long)W);
+  GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt_c1_tc: bad extent");
+  GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
+             "convt_c1_tc: channel groups (%d + %d) must be even in total", cg0, cg1);
+  GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "convt_c1_tc: grid too large");
+  GB_REQUIRE(aligned16(src0) && aligned16(wpack) && ((uintptr_t)out & 7) == 0 && (!src1 || aligned16(src1)), GENRE_B200_EALIGN,
+             "convt_c1_tc: alignment");
+  ConvTParams p;
+  p.src0 = src0; p.src1 = src1; p.cg0 = cg0; p.cg1 = cg1;
+  p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
+  p.wpack = wpack; p.scale = bias; p.shift = bias; p.slope = 1.0f; p.out = out; p.cgo = 1;
+  p.srcpar_cgs = 0;
+  p.act_sigmoid = act_sigmoid;
+  p.base[0] = p.base[1] = 1;
+  cudaStream_t st = as_stream(stream);
+  if (W == 64) return launch_convt_c1<8>(p, st);
+  if (W == 32) return launch_convt_c1<4>(p, st);
+  return launch_convt_c1<2>(p, st);
 }
 
 // Stride-1 convolution with T taps per dimension on channel-blocked activations (same kernel, one output class):

@@ -177,6 +177,22 @@ from_blocked_kernel(const float4 *__restrict__ src, float *__restrict__ dst, int
   }
 }
 
+// blocked fp32 groups of 4 -> blocked fp16 groups of 8 (channel padding to a multiple of 8 is zero-filled)
+__global__ void __launch_bounds__(LY_THREADS)
+regroup_f16_kernel(const float4 *__restrict__ src, uint4 *__restrict__ dst, int cg4, int cg8, size_t plane, size_t units) {
+  for (size_t u = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; u < units; u += (size_t)gridDim.x * LY_THREADS) {
+    const size_t hw = u % plane;
+    size_t r = u / plane;
+    const int g = (int)(r % cg8);
+    r /= cg8;  // b * D + d
+    const float4 *s = src + (r * cg4 + 2 * g) * plane + hw;
+    const float4 a = __ldg(s);
+    const float4 b = 2 * g + 1 < cg4 ? __ldg(s + plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    store_unit<8>(dst, u, x);
+  }
+}
+
 static unsigned ly_grid(size_t n) {
   const size_t blocks = (n + LY_THREADS - 1) / LY_THREADS;
   const size_t cap = 148ull * 8 * 16;  // grid-stride beyond ~16 waves of 8 CTAs per SM
@@ -239,4 +255,16 @@ extern "C" int genre_b200_blocked_to_ncdhw(const float *src, int cg, int64_t B, 
   from_blocked_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, dst, (int)C, cg, (int)D,
                                                                            (int)H, (int)W, units);
   return check_launch("from_blocked kernel");
+}
+
+// blocked fp32 [BD][cg4][H][W][4] -> blocked fp16 [BD][(cg4+1)/2][H][W][8] (operand of the fp16 tensor-core kernels)
+extern "C" int genre_b200_blocked_f32_to_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst,
+                                             void *stream) {
+  GB_REQUIRE(src && dst && cg4 > 0 && BD > 0 && H > 0 && W > 0, GENRE_B200_EINVAL, "blocked_f32_to_f16: bad argument");
+  GB_REQUIRE(aligned16(src) && aligned16(dst), GENRE_B200_EALIGN, "blocked_f32_to_f16: alignment");
+  const int cg8 = (cg4 + 1) / 2;
+  const size_t plane = (size_t)(H * W), units = (size_t)BD * cg8 * plane;
+  regroup_f16_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, (uint4 *)dst, cg4, cg8, plane,
+                                                                          units);
+  return check_launch("regroup_f16 kernel");
 }

@@ -37,7 +37,7 @@ class ConvTranspose3d(nn.ConvTranspose3d):
 
 
 class FusedSequential(nn.Sequential):
-    """nn.Sequential (same state_dict keys) whose CUDA forward hands conv [-> BatchNorm3d] -> ReLU/LeakyReLU runs to
+    """nn.Sequential (same state_dict keys) whose CUDA forward hands conv [-> BatchNorm3d] -> ReLU/LeakyReLU/Sigmoid runs to
     ops_conv.fused_block: one kernel with the eval-mode normalisation and the activation in its epilogue.  Anything
     not covered (training-mode BN, autograd, unsupported shapes, CPU) runs module by module like nn.Sequential."""
 
@@ -50,7 +50,7 @@ class FusedSequential(nn.Sequential):
                 j = i + 1
                 bn = mods[j] if j < len(mods) and isinstance(mods[j], nn.BatchNorm3d) else None
                 j += bn is not None
-                act = mods[j] if j < len(mods) and isinstance(mods[j], (nn.ReLU, nn.LeakyReLU)) else None
+                act = mods[j] if j < len(mods) and isinstance(mods[j], (nn.ReLU, nn.LeakyReLU, nn.Sigmoid)) else None
                 if act is not None:
                     y = ops_conv.fused_block(x, m, bn, act)
                     if y is not None:

@@ -30,7 +30,8 @@ ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
 #   convt_c1_convert   the 1-channel layer when its input must first be converted; FP32-pipe kernel, so only up to
 #                      C1_MAX_CIN input channels (VoxelDecoder's 32 -> 1 wins, VoxelGenerator's 64 -> 1 does not)
 # GENRE_B200_CONV_POLICY = comma list restricts the set ("all" = everything, the default).
-_all_policy = {"convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert"}
+#   convt_c1_tc   the 1-channel layer on the tensor cores (3 union taps, 8 output classes as N columns); tried first
+_all_policy = {"convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc"}
 _default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
@@ -182,6 +183,31 @@ def pack_convt_merged_weights(weight, cpad, group=4):
                         weq[:, c0:c0 + cout, pz, :, uy, ux] = weight[:, :, k0[pz]::2, k0[py] + 2 * ty, k0[px] + 2 * tx]
     sub = weq.reshape(cin // (2 * g), 2, g, n // 8, 8, 2, t, tu, tu)    # (kc, kk, e, ng, r, pz, tz, uy, ux)
     out = sub.permute(5, 6, 0, 7, 8, 1, 3, 4, 2).contiguous()           # (pz, tz, kc, uy, ux, kk, ng, r, e)
+    return out.half() if g == 8 else out
+
+
+def pack_convt_c1_tc_weights(weight, segments, group=4):
+    """ConvTranspose3d weight [Cin, 1, 4, 4, 4] (stride 2, padding 1) for kernel MODE 4: [3 z-tap][chunk][9 taps][2][2][8][g].
+    N = 16 columns, n = (qz*2+qy)*2+qx < 8 the output classes; union tap u reads input j + 1 - u and serves class q as its
+    tap t = u - 1 + q (kernel index k = (q+1)%2 + 2t).  `segments` = [(real channels, padded channels), ...] of the
+    concatenated sources: padded rows are zero."""
+    g = group
+    kmap = {(0, 1): 1, (0, 2): 3, (1, 0): 0, (1, 1): 2}                  # (q, u) -> k
+    ktot = sum(pc for _, pc in segments)
+    weq = weight.new_zeros((ktot, 16, 3, 3, 3))
+    rows, c0, r0 = [], 0, 0
+    for real, padded in segments:
+        rows.append((r0, c0, real))
+        c0, r0 = c0 + real, r0 + padded
+    assert c0 == weight.shape[0] and ktot % (2 * g) == 0
+    for (qz, uz), kz in kmap.items():
+        for (qy, uy), ky in kmap.items():
+            for (qx, ux), kx in kmap.items():
+                n = (qz * 2 + qy) * 2 + qx
+                for r0, c0, real in rows:
+                    weq[r0:r0 + real, n, uz, uy, ux] = weight[c0:c0 + real, 0, kz, ky, kx]
+    sub = weq.reshape(ktot // (2 * g), 2, g, 2, 8, 3, 3, 3)               # (kc, kk, e, ng, r, tz, ty, tx)
+    out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()
     return out.half() if g == 8 else out
 
 
@@ -479,6 +505,56 @@ def conv3d(x, m, bn=None, slope=None):
     return from_blocked(out, b, cout)
 
 
+def _operand_of(x):
+    """blocked operand of the tensor-core kernels for activation x (NCDHW tensor or BlockedActivation) in the current
+    PRECISION, reusing the fp32 blocked twin a previous custom layer left behind; (operand, padded channels) or None"""
+    c = x.shape[1]
+    twin = _cached_blocked(x)
+    if not _f16():
+        if twin is not None:
+            return twin, twin.shape[1] * 4
+        return (to_blocked(x, 4), c) if c % 4 == 0 and not isinstance(x, BlockedActivation) else None
+    if twin is not None:
+        bd, cg4, h, w, _ = twin.shape
+        out = torch.empty((bd, (cg4 + 1) // 2, h, w, 8), device=twin.device, dtype=torch.float16)
+        _lib.call("genre_b200_blocked_f32_to_f16", twin.data_ptr(), cg4, bd, h, w, out.data_ptr(), _lib.stream_ptr(twin))
+        return out, out.shape[1] * 8
+    return (to_blocked(x, 8, torch.float16), c) if c % 8 == 0 and not isinstance(x, BlockedActivation) else None
+
+
+def convt_c1_tc(inputs, m, sigmoid=False):
+    """ConvTranspose3d(Cin -> 1, k4, s2, p1) over the channel concatenation of `inputs` on the tensor cores (MODE 4);
+    NCDHW [B,1,2D,2H,2W] or None if not covered."""
+    x0 = inputs[0]
+    if not ("convt_c1_tc" in POLICY and ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
+            and tuple(m.padding) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1)
+            and m.groups == 1 and m.out_channels == 1 and len(inputs) <= 2
+            and all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 5 and t.shape[2:] == x0.shape[2:] for t in inputs)
+            and x0.shape[4] in (16, 32, 64) and x0.shape[3] % 16 == 0 and _no_autograd(*inputs, m.weight, m.bias)):
+        return None
+    ops = [_operand_of(t) for t in inputs]
+    if any(o is None for o in ops):
+        return None
+    g = _group()
+    segments = tuple((t.shape[1], o[1]) for t, o in zip(inputs, ops))
+    if sum(pc for _, pc in segments) % (2 * g) != 0:
+        return None
+    wpack = _cached_pack(m, ("c1_tc", segments, g), lambda wt: pack_convt_c1_tc_weights(wt, segments, g))
+    b, _, d, h, w = x0.shape
+    if m.bias is not None:
+        bias = m.bias.detach()
+    else:
+        bias = m.__dict__.get("_gb_zero_bias")
+        if bias is None or bias.device != x0.device:
+            bias = m.__dict__["_gb_zero_bias"] = torch.zeros(1, device=x0.device)
+    out = torch.empty((b, 1, 2 * d, 2 * h, 2 * w), device=x0.device, dtype=torch.float32)
+    s1 = ops[1][0] if len(ops) > 1 else None
+    _lib.call("genre_b200_convt_c1_tc_forward", ops[0][0].data_ptr(), ops[0][0].shape[1], s1.data_ptr() if s1 is not None else None,
+              s1.shape[1] if s1 is not None else 0, b, d, h, w, wpack.data_ptr(), 1 if g == 8 else 0, bias.data_ptr(),
+              1 if sigmoid else 0, out.data_ptr(), _lib.stream_ptr(out))
+    return out
+
+
 def _has_blocked(x):
     return _cached_blocked(x) is not None
 
@@ -515,6 +591,10 @@ def convt_c1(src0, src1, batch, m):
 def conv_transpose3d(x, m, bn=None, slope=None):
     """ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> ReLU / LeakyReLU(slope)]; None if not covered
     (the caller then runs the plain modules)."""
+    if bn is None and slope is None and m.out_channels == 1:
+        y = convt_c1_tc((x,), m)
+        if y is not None:
+            return y
     if (bn is None and slope is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
             and _convt_c1_supported(x.shape[1], x.shape[2:], m, (x,)) and _no_autograd(x, m.weight, m.bias)):
         return convt_c1(_blocked_f32(x), None, x.shape[0], m)
@@ -528,6 +608,8 @@ def conv_transpose3d(x, m, bn=None, slope=None):
 def fused_block(x, conv, bn, act):
     """conv [-> BatchNorm3d] -> ReLU/LeakyReLU as ONE kernel launch when the conv has a custom kernel: the normalisation
     and activation passes over the activation (0.9 ms of VoxelGenerator's 64^3 stage at B=16) disappear into the epilogue."""
+    if isinstance(act, torch.nn.Sigmoid):   # VoxelGenerator's last stage: ConvT(-> 1 channel) -> Sigmoid
+        return convt_c1_tc((x,), conv, sigmoid=True) if bn is None and isinstance(conv, torch.nn.ConvTranspose3d) else None
     slope = 0.0 if isinstance(act, torch.nn.ReLU) else float(act.negative_slope)
     if isinstance(conv, torch.nn.ConvTranspose3d):
         return conv_transpose3d(x, conv, bn, slope)
@@ -537,6 +619,10 @@ def fused_block(x, conv, bn, act):
 def deconv_skip(x, skip, conv, bn=None, slope=None, keep_blocked=False):
     """cat(x, skip) -> ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> LeakyReLU(slope)] with the
     concatenation walked as two K ranges instead of being materialised.  None if not covered."""
+    if bn is None and conv.out_channels == 1:
+        y = convt_c1_tc((x, skip), conv)
+        if y is not None:
+            return y
     if (bn is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
             and x.shape[1] % 4 == 0 and skip.shape[1] % 4 == 0
             and _convt_c1_supported(x.shape[1] + skip.shape[1], x.shape[2:], conv, (x, skip))

@@ -236,6 +236,14 @@ int genre_b200_conv3d_k8s2_s4d_forward(const void *src, int cg, int64_t B, int64
                                        const float *scale, const float *shift, float slope,
                                        float *out, int cgo, void *stream);
 
+/* ConvTranspose3d(Cin -> 1, k 4, s 2, p 1) on the tensor cores: 3 union taps per dimension, the 8 output classes as
+ * N columns, bias [1] (device) and optional sigmoid in the epilogue, NCDHW fp32 output [B][2D][2H][2W].  Same layers
+ * as genre_b200_convt_c1_forward (the FP32-pipe variant); wpack [3][chunk][9][2][2][8][g].  W in {16,32,64}. */
+int genre_b200_convt_c1_tc_forward(const void *src0, int cg0, const void *src1, int cg1,
+                                   int64_t B, int64_t D, int64_t H, int64_t W,
+                                   const void *wpack, int f16, const float *bias, int act_sigmoid,
+                                   float *out, void *stream);
+
 /* Layout boundary of the convolution kernels: contiguous NCDHW fp32 (what networks/networks.py's modules exchange,
  * e.g. Unet_3D.forward networks.py:170-190) <-> channel-blocked [B*D][C/g][H][W][g] (16 bytes per unit).
  *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1);
@@ -248,6 +256,10 @@ int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t 
 /* blocked fp32 [B*D][cg][H][W][4] -> contiguous NCDHW [B,C,D,H,W], 4*(cg-1) < C <= 4*cg (channel padding dropped) */
 int genre_b200_blocked_to_ncdhw(const float *src, int cg, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
                                 float *dst, void *stream);
+
+/* blocked fp32 [BD][cg4][H][W][4] -> blocked fp16 [BD][(cg4+1)/2][H][W][8], channel padding zero-filled: turns the
+ * fp32 output of one tensor-core layer into the fp16 operand of the next without going through NCDHW */
+int genre_b200_blocked_f32_to_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst, void *stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,28 @@ def test_pack_convt_merged_weights(k):
     assert torch.allclose(out, ref, atol=1e-5)
 
 
+def test_pack_convt_c1_tc_weights_two_padded_sources():
+    """MODE 4: ConvT(Cin -> 1, k4 s2 p1) with the 8 output classes as N columns over two zero-padded K segments"""
+    torch.manual_seed(8)
+    c0, c1, g = 5, 3, 4
+    wt = torch.randn(c0 + c1, 1, 4, 4, 4)
+    xa, xb_ = torch.randn(2, c0, 3, 4, 5), torch.randn(2, c1, 3, 4, 5)
+    ref = F.conv_transpose3d(torch.cat((xa, xb_), 1).double(), wt.double(), stride=2, padding=1)
+    segments = ((c0, 8), (c1, 8))
+    wp = ops_conv.pack_convt_c1_tc_weights(wt, segments, g)
+    assert wp.shape == (3, 2, 3, 3, 2, 2, 8, 4)
+    pad = lambda t, c: F.pad(t, (0, 0, 0, 0, 0, 0, 0, c - t.shape[1]))
+    blocked = torch.cat((ops_conv.to_blocked(pad(xa, 8), g), ops_conv.to_blocked(pad(xb_, 8), g)), dim=1)
+    y = _taps_gemm(blocked.contiguous(), 2, wp, 1, 1, 1)                              # [B,D,H,W,16]
+    out = torch.zeros_like(ref)
+    for qz in (0, 1):
+        for qy in (0, 1):
+            for qx in (0, 1):
+                out[:, 0, qz::2, qy::2, qx::2] = y[..., (qz * 2 + qy) * 2 + qx]
+    assert torch.allclose(out, ref, atol=1e-5)
+    assert y[..., 8:].abs().max() == 0
+
+
 def test_pack_conv_k8s2_weights_space_to_depth():
     torch.manual_seed(3)
     cin, cout, npad = 2, 5, 8

@@ -165,6 +165,7 @@ def test_tf32_switch_is_honoured():
 
 @pytest.mark.parametrize("cin,b,d,h,w", [(8, 1, 3, 8, 8), (40, 2, 4, 16, 32), (32, 1, 5, 12, 20)])
 def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
+    ops_conv.POLICY = ops_conv.POLICY - {"convt_c1_tc"}      # this test is about the FP32-pipe kernel
     torch.manual_seed(cin + w)
     m = nets.ConvTranspose3d(cin, 1, 4, 2, 1).to(DEV)
     x = torch.randn(b, cin, d, h, w, device=DEV)
@@ -178,7 +179,33 @@ def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
     assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())   # plain fp32 FMAs
 
 
+@pytest.mark.parametrize("chans,b,d,h,w,sigmoid", [((48,), 2, 3, 16, 32, False), ((32,), 1, 2, 32, 64, False), ((64,), 1, 2, 16, 16, True),
+                                                    ((20, 20), 1, 4, 16, 16, False), ((24, 8), 2, 2, 32, 32, False)])
+def test_convt_c1_tensor_core_vs_torch(chans, b, d, h, w, sigmoid):
+    """MODE 4: ConvT(Cin -> 1) as 27 union taps x 8 output classes on the tensor cores; one or two (skip) sources, the
+    20-channel ones arriving as blocked twins of a previous custom layer (zero-padded to the operand group size)"""
+    torch.manual_seed(sum(chans) + w)
+    m = nets.ConvTranspose3d(sum(chans), 1, 4, 2, 1).to(DEV)
+    xs = []
+    for c in chans:
+        t = torch.randn(b, c, d, h, w, device=DEV)
+        if c % 8:   # give it the blocked fp32 twin a custom layer would have attached
+            t = ops_conv.from_blocked(ops_conv.to_blocked(t, 4), b, c)
+        xs.append(t)
+    with torch.no_grad():
+        y = ops_conv.convt_c1_tc(tuple(xs), m, sigmoid)
+        assert y is not None
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv_transpose3d(torch.cat(xs, 1), m.weight, m.bias, stride=2, padding=1)
+        torch.backends.cudnn.allow_tf32 = True
+        if sigmoid:
+            ref = torch.sigmoid(ref)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_dec6_two_source_path_vs_torch():
+    ops_conv.POLICY = ops_conv.POLICY - {"convt_c1_tc"}
     torch.manual_seed(3)
     blk = nets.Deconv3d_skip(40, 1, 4, 2, 1, 0, is_activate=False).to(DEV).eval()
     x, s = torch.randn(1, 20, 4, 16, 16, device=DEV), torch.randn(1, 20, 4, 16, 16, device=DEV)
