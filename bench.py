@@ -321,8 +321,8 @@ def run_b200(args):
                "host_cpus": os.cpu_count()}
 
     # ---- secondary (rank 0, N=1): the GenRe 3D hot path at batch 16, informational ------------------------------------
-    secondary = None
-    if rank == 0 and world == 1:
+    secondary = None   # GENRE_B200_BENCH_SECONDARY=0 skips it (used for the ncu launch list of the headline step alone)
+    if rank == 0 and world == 1 and os.environ.get("GENRE_B200_BENCH_SECONDARY", "1") != "0":
         try:
             secondary = genre3d_path(torch, dev)
         except Exception as e:  # informational only: never fail the headline measurement

@@ -178,8 +178,13 @@ struct ConvTCfg {
   static constexpr int B_TAP_BYTES = 2 * (NPAD / 8) * 128;     // one (y,x) tap: [2 kcore][NPAD/8][8 rows][16 B]
   static constexpr int B_BYTES = T * T * B_TAP_BYTES;
   static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 127) / 128) * 128;
-  static constexpr int STAGES = (218 * 1024) / STAGE_BYTES > 6 ? 6 : (218 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = MT * NPAD <= 32 ? 32 : MT * NPAD <= 64 ? 64 : MT * NPAD <= 128 ? 128 : MT * NPAD <= 256 ? 256 : 512;
+  // Two CTAs per SM whenever TMEM (<= 256 columns each) and shared memory (<= ~112 KB each) allow: one CTA's prologue
+  // (TMEM alloc, pipeline fill) and epilogue (TMEM drain, stores) then overlap the other's MMA stream.
+  static constexpr int S_ALONE = (218 * 1024) / STAGE_BYTES > 6 ? 6 : (218 * 1024) / STAGE_BYTES;
+  static constexpr int S_PAIR = (112 * 1024) / STAGE_BYTES > 6 ? 6 : (112 * 1024) / STAGE_BYTES;
+  static constexpr bool PAIR = TMEM_COLS <= 256 && S_PAIR >= 2;
+  static constexpr int STAGES = PAIR ? S_PAIR : S_ALONE;
   static constexpr int POS = PY * PX;
   static constexpr int POS_PER_THREAD = (POS + CT_PRODUCERS - 1) / CT_PRODUCERS;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
@@ -597,10 +602,11 @@ extern "C" int genre_b200_conv3d_k8s2_s4d_forward(const void *src_, int cg, int6
   const float *src = (const float *)src_, *wpack = (const float *)wpack_;
   g_conv_f16 = f16 != 0;
   GB_REQUIRE(src && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: null pointer");
-  GB_REQUIRE(npad == 160, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: npad %d unsupported (160 = 8 classes x 20 channels)", npad);
+  GB_REQUIRE(npad == 160 || npad == 80, GENRE_B200_EINVAL,
+             "conv3d_k8s2_s4d: npad %d unsupported (160 = 8 classes x 20 channels, or 80 = 4 (y,x) classes per z class)", npad);
   GB_REQUIRE(W > 0 && W % 16 == 0 && H > 0 && H % CT_BY == 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: bad extent");
   GB_REQUIRE(cg > 0 && cg % CT_KCG == 0, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: channel groups must be even");
-  GB_REQUIRE(cgo > 0 && 32 * cgo <= npad, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: too many output channels");
+  GB_REQUIRE(cgo > 0 && cgo <= 5, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: too many output channels");
   GB_REQUIRE(B * D * (H / CT_BY) * (W / 16) < (1ll << 31), GENRE_B200_EINVAL, "conv3d_k8s2_s4d: grid too large");
   GB_REQUIRE(aligned16(src) && aligned16(wpack) && aligned16(out), GENRE_B200_EALIGN, "conv3d_k8s2_s4d: alignment");
   ConvTParams p;
@@ -609,6 +615,9 @@ extern "C" int genre_b200_conv3d_k8s2_s4d_forward(const void *src_, int cg, int6
   p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
   p.srcpar_cgs = 0;
   p.base[0] = p.base[1] = 1;  // input cell = j + 1 - t
+  // npad 80: the z class moves to blockIdx.y (MODE 2 with 3 z taps per class; wpack [2 qz][3][chunk][9][2][10][8][g]):
+  // twice the MMAs of the 8-class form, but 256 TMEM columns and half the weight bytes per stage let two CTAs share an SM
+  if (npad == 80) return launch_convt_merged<3, 3, 80, 2>(p, as_stream(stream));
   return launch_conv_merged8<3, 160, 2>(p, as_stream(stream));
 }
 

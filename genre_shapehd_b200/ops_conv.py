@@ -43,6 +43,8 @@ K4S2_MIN_CIN = 8
 PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "f16")
 # k=8 ConvTranspose3d with Cout <= 20 (Unet_3D.dec5): merge the four (y,x) parity classes into one N=80 MMA stream
 MERGE_PARITIES = os.environ.get("GENRE_B200_CONV_MERGE", "1") != "0"
+# Unet_3D.enc1 (4x space-to-depth form): z class on blockIdx.y (N = 80, two CTAs per SM) instead of all 8 classes in N = 160
+S4D_SPLIT_Z = os.environ.get("GENRE_B200_S4D_SPLIT_Z", "0") != "0"   # measured: 0.88 vs 0.80 ms, so off
 
 
 def _f16():
@@ -305,7 +307,7 @@ def space_to_depth4_blocked(x, group=4, dtype=None):
     return _permuted_copy(t, dtype)
 
 
-def pack_conv_k8s2_s4d_weights(weight, cpad, group=4):
+def pack_conv_k8s2_s4d_weights(weight, cpad, group=4, split_z=False):
     """Conv3d weight [Cout, Cin, 8, 8, 8] (stride 2, padding 3) -> the 3-tap stride-1 convolution over the 64*Cin
     4x-space-to-depth channels whose N = 8*cpad columns are the 8 output classes q of the 2x finer output grid:
     [3 z-tap][chunk][9 taps][2][N/8][8][g].  Per dimension: output 2j+q reads input 4j + 2q - 3 + k; coarse cell
@@ -324,6 +326,10 @@ def pack_conv_k8s2_s4d_weights(weight, cpad, group=4):
     full = weight[:, :, kz, ky, kx] * (vz & vy & vx).to(weight.dtype)      # [co, c, qz,tz,rz, qy,ty,ry, qx,tx,rx]
     weq = full.permute(1, 4, 7, 10, 2, 5, 8, 0, 3, 6, 9)                  # c rz ry rx | qz qy qx co | tz ty tx
     weq = torch.nn.functional.pad(weq, (0, 0, 0, 0, 0, 0, 0, cpad - cout)).reshape(cin * 64, n, 3, 3, 3)
+    if split_z:   # [2 qz] x the 4-class (y,x) form: N = 4*cpad columns per z class
+        sub = weq.reshape(cin * 64 // (2 * g), 2, g, 2, n // 16, 8, 3, 3, 3)   # (kc, kk, e, qz, ng, r, tz, ty, tx)
+        out = sub.permute(3, 6, 0, 7, 8, 1, 4, 5, 2).contiguous()              # (qz, tz, kc, ty, tx, kk, ng, r, e)
+        return out.half() if g == 8 else out
     sub = weq.reshape(cin * 64 // (2 * g), 2, g, n // 8, 8, 3, 3, 3)      # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                # (tz, kc, ty, tx, kk, ng, r, e)
     return out.half() if g == 8 else out
@@ -479,12 +485,12 @@ def conv3d(x, m, bn=None, slope=None):
         if aff is None:
             return None
         g, b, cout = _group(), x.shape[0], m.out_channels
-        wpack = _cached_pack(m, ("k8s2_s4d", 20, g), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g))
+        wpack = _cached_pack(m, ("k8s2_s4d", 20, g, S4D_SPLIT_Z), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g, S4D_SPLIT_Z))
         xb = space_to_depth4_blocked(x, g, torch.float16 if _f16() else None)
         bd, cg, h, w, _ = xb.shape
         cgo = (cout + 3) // 4
         out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=x.device, dtype=torch.float32)
-        _lib.call("genre_b200_conv3d_k8s2_s4d_forward", xb.data_ptr(), cg, b, bd // b, h, w, wpack.data_ptr(), 160,
+        _lib.call("genre_b200_conv3d_k8s2_s4d_forward", xb.data_ptr(), cg, b, bd // b, h, w, wpack.data_ptr(), 80 if S4D_SPLIT_Z else 160,
                   1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
                   out.data_ptr(), cgo, _lib.stream_ptr(x))
         return from_blocked(out, b, cout)

@@ -126,6 +126,12 @@ def test_pack_conv_k8s2_s4d_weights_merged_classes():
                 c0 = ((qz * 2 + qy) * 2 + qx) * cpad
                 out[:, :, qz::2, qy::2, qx::2] = y[..., c0:c0 + cout].permute(0, 4, 1, 2, 3)
     assert torch.allclose(out, ref, atol=1e-5)
+    # z class split off (kernel MODE 2 with 3 z taps per class): the same columns, regrouped
+    wz = ops_conv.pack_conv_k8s2_s4d_weights(wt, cpad, 4, split_z=True)
+    assert wz.shape[:2] == (2, 3) and wz.shape[6] * 8 == 4 * cpad
+    for qz in (0, 1):
+        yz = _taps_gemm(xb, 2, wz[qz], 1, 1, 1)
+        assert torch.allclose(yz, y[..., qz * 4 * cpad:(qz + 1) * 4 * cpad], atol=1e-9)
 
 
 def test_pack_conv_k4s2_weights_parity_sources():

@@ -139,6 +139,25 @@ def test_conv3d_k8s2_via_space_to_depth_vs_torch(cin, cout, b, d, h, w):
     assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("split_z", [True, False])
+def test_conv3d_k8s2_s4d_both_class_layouts(split_z):
+    """Unet_3D.enc1's 4x space-to-depth form: all 8 classes in N=160 (MODE 3) or the z class on blockIdx.y (MODE 2, N=80)"""
+    torch.manual_seed(13)
+    m = nets.Conv3d(2, 20, 8, 2, 3).to(DEV)
+    x = torch.randn(2, 2, 8, 64, 128, device=DEV)
+    old = ops_conv.S4D_SPLIT_Z
+    try:
+        ops_conv.S4D_SPLIT_Z = split_z
+        with torch.no_grad():
+            y = ops_conv.conv3d(x, m)
+            torch.backends.cudnn.allow_tf32 = False
+            ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=3)
+            torch.backends.cudnn.allow_tf32 = True
+    finally:
+        ops_conv.S4D_SPLIT_Z = old
+    assert y is not None and (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
 def test_conv_block_fused_bn_leaky_vs_torch():
     torch.manual_seed(11)
     blk = nets.Conv3d_block(2, 20, 8, 2, 3).to(DEV).eval()
