@@ -153,7 +153,7 @@ vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ov
 
 template <bool VEC, bool WRITE_CNT>
 static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long long nvox, float *tdf, float *cnt,
-                        float alpha, float beta, float bg, cudaStream_t st) {
+                        float alpha, float beta, float bg, cudaStream_t st, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)w.ntiles, (unsigned)n_maps);
   cfg.blockDim = dim3(VOX_SPLAT_THREADS);
@@ -163,7 +163,7 @@ static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long l
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap this launch with the project kernel's tail
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 1 : 0;  // stand-alone launches (stage entry point, used for timing) keep plain stream ordering
   const uint2 *buckets = w.buckets, *ovf = w.ovf;
   const unsigned *counts = w.counts, *ovf_count = w.ovf_count;
   const long long Pll = (long long)P;
@@ -179,15 +179,15 @@ static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long l
 }
 
 int vox_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, int res, float *tdf, float *cnt, float alpha,
-              float beta, float bg, cudaStream_t st) {
+              float beta, float bg, cudaStream_t st, bool pdl) {
   const long long nvox = (long long)res * res * res;
   const bool vec = (nvox % 4 == 0) && aligned16(tdf) && (!cnt || aligned16(cnt));
   if (vec) {
-    return cnt ? launch_splat<true, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st)
-               : launch_splat<true, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st);
+    return cnt ? launch_splat<true, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl)
+               : launch_splat<true, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl);
   }
-  return cnt ? launch_splat<false, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st)
-             : launch_splat<false, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st);
+  return cnt ? launch_splat<false, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl)
+             : launch_splat<false, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl);
 }
 
 // arguments shared by both back-projections
@@ -217,5 +217,5 @@ extern "C" int genre_b200_voxelize_stage_splat(int64_t n_maps, int64_t P, int re
   gb::VoxWorkspace w;
   GB_REQUIRE(gb::vox_carve(workspace, workspace_bytes, n_maps, P, res, &w), GENRE_B200_EWORKSPACE,
              "workspace too small or misaligned (need %zu bytes)", gb::vox_workspace_bytes(n_maps, P, res));
-  return gb::vox_splat(w, n_maps, P, res, tdf, cnt, hit_alpha, hit_beta, background, gb::as_stream(stream));
+  return gb::vox_splat(w, n_maps, P, res, tdf, cnt, hit_alpha, hit_beta, background, gb::as_stream(stream), false);
 }
