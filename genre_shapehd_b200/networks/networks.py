@@ -33,6 +33,8 @@ class Conv3d(nn.Conv3d):
 class ConvTranspose3d(nn.ConvTranspose3d):
     def forward(self, x, output_size=None):
         y = ops_conv.conv_transpose3d(x, self) if output_size is None else None
+        if y is None and output_size is None and x.is_cuda:
+            y = ops_conv.gemm_conv(x, self)
         return y if y is not None else super().forward(x, output_size)
 
 

@@ -31,7 +31,8 @@ ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
 #                      C1_MAX_CIN input channels (VoxelDecoder's 32 -> 1 wins, VoxelGenerator's 64 -> 1 does not)
 # GENRE_B200_CONV_POLICY = comma list restricts the set ("all" = everything, the default).
 #   convt_c1_tc   the 1-channel layer on the tensor cores (3 union taps, 8 output classes as N columns); tried first
-_all_policy = {"convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc"}
+#   gemm          ConvTranspose3d on a 1^3 input (dec1, the decoders' first layer) as one cuBLAS GEMM (0.34 -> 0.085 ms)
+_all_policy = {"convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
 _default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
@@ -609,6 +610,25 @@ def conv_transpose3d(x, m, bn=None, slope=None):
         return None
     y = convt3d_s2_blocked(_to_operand(x), None, x.shape[0], m, bn, 1.0 if slope is None else slope)
     return None if y is None else from_blocked(y, x.shape[0], m.out_channels)
+
+
+def gemm_conv(x, m):
+    """A ConvTranspose3d(k, s=1, p=0) on a 1^3 input IS a plain matrix product,
+          out[b, co, :] = sum_ci x[b, ci] * W[ci, co, :]   =   x[B,Cin] @ W[Cin, Cout*k^3],
+    bound by reading the weights once (105 MB for Unet_3D.dec1 networks.py:162; VoxelDecoder/VoxelGenerator main.0
+    :40,:79): handed to cuBLAS it takes 0.085 ms at B=16 where cuDNN's dgrad engine takes 0.34 ms.  Pure torch ops:
+    differentiable, so training takes this route too; fp32 unless torch.backends.cuda.matmul.allow_tf32.
+    (The mirror case, Conv3d(k) from k^3 to 1^3 = Unet_3D.enc6, was measured too: the skinny split-K GEMM is slower
+    than cuDNN there, 0.134 vs 0.076 ms, so it is not routed.)"""
+    if not (ENABLED and "gemm" in POLICY and x.is_cuda and x.dim() == 5 and x.dtype == torch.float32 and m.groups == 1
+            and isinstance(m, torch.nn.ConvTranspose3d) and tuple(m.stride) == (1, 1, 1) and tuple(m.padding) == (0, 0, 0)
+            and tuple(m.dilation) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(x.shape[2:]) == (1, 1, 1)):
+        return None
+    b = x.shape[0]
+    y = (x.reshape(b, m.in_channels) @ m.weight.reshape(m.in_channels, -1)).view(b, m.out_channels, *m.kernel_size)
+    if m.bias is not None:
+        y = y + m.bias.view(1, -1, 1, 1, 1)
+    return y
 
 
 def fused_block(x, conv, bn, act):

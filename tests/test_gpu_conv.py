@@ -291,3 +291,26 @@ def test_fused_sequential_matches_module_by_module(name):
         ref = net(x)
         torch.backends.cudnn.allow_tf32 = True
     assert (y - ref).abs().max().item() <= 2e-2 * max(1e-3, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("convt", 1280, 320), ("convt", 200, 512)])
+def test_degenerate_convolutions_as_gemm(kind, cin, cout):
+    """1^3 -> 4^3 transposed convolutions routed to one cuBLAS GEMM: forward and gradients against the cuDNN module"""
+    torch.manual_seed(cin)
+    if kind == "convt":
+        m, x = nets.ConvTranspose3d(cin, cout, 4, 1, 0).to(DEV), torch.randn(3, cin, 1, 1, 1, device=DEV, requires_grad=True)
+    else:
+        m, x = nets.Conv3d(cin, cout, 4, 1, 0).to(DEV), torch.randn(3, cin, 4, 4, 4, device=DEV, requires_grad=True)
+    y = ops_conv.gemm_conv(x, m)
+    assert y is not None
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.ConvTranspose3d.forward(m, x) if kind == "convt" else torch.nn.Conv3d.forward(m, x)
+    torch.backends.cudnn.allow_tf32 = True
+    assert y.shape == ref.shape and (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    g = torch.randn_like(ref)
+    gx, gw = torch.autograd.grad(y, (x, m.weight), g)
+    torch.backends.cudnn.allow_tf32 = False
+    rx, rw = torch.autograd.grad(ref, (x, m.weight), g)
+    torch.backends.cudnn.allow_tf32 = True
+    assert (gx - rx).abs().max().item() <= 1e-4 * max(1.0, rx.abs().max().item())
+    assert (gw - rw).abs().max().item() <= 1e-4 * max(1.0, rw.abs().max().item())
