@@ -343,8 +343,10 @@ def run_b200(args):
 
 def genre3d_path(torch, dev, batch=16, reps=5):
     """BASELINE configs[2] without the two 2D U-ResNets (out of scope): cam_bp -> render_spherical -> sph_pad ->
-    backproject_spherical glue -> clamp/cat -> Unet_3D (eval), glue lines as in the frozen caller
-    (depth_pred_with_sph_inpaint.py:120-126, genre_full_model.py:120-143)."""
+    backproject_spherical glue -> clamp/cat -> Unet_3D (eval).  Timed twice: with the glue lines of the frozen callers
+    (depth_pred_with_sph_inpaint.py:120-126, genre_full_model.py:120-143) on the drop-in ops, and with the opt-in
+    fused glue (genre_shapehd_b200/fused.py)."""
+    from genre_shapehd_b200.fused import GenRe3DGlue
     from genre_shapehd_b200.synth import bench_depth_batch
     from toolbox.cam_bp.cam_bp.functions import SphericalBackProjection
     from toolbox.cam_bp.cam_bp.modules.camera_backprojection_module import Camera_back_projection_layer
@@ -354,26 +356,35 @@ def genre3d_path(torch, dev, batch=16, reps=5):
     proj, rend = Camera_back_projection_layer(), render_spherical().to(dev)
     grid = gen_sph_grid().to(dev).expand(batch, -1, -1, -1, -1)
     unet = nets.Unet_3D().to(dev).eval()
+    glue = GenRe3DGlue().to(dev)
 
-    def step():
+    def step_callers():
         pd = proj(depth)
         sph = sph_pad(rend(torch.clamp(pd * 50, 1e-5, 1 - 1e-5)), 16)
         df, cnt = SphericalBackProjection.apply(1 - sph[:, :, 16:144, 16:144], grid, 128)
         ps = (-df + 1 / 128) * 128 * torch.clamp(cnt, 0, 1)
-        return unet(torch.cat((ps, torch.clamp(pd / 50, 1e-5, 1 - 1e-5)), dim=1))
-    with torch.no_grad():
-        for _ in range(2):
-            step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+        return unet(torch.cat((ps, torch.clamp((pd * 50) / 50, 1e-5, 1 - 1e-5)), dim=1))
+
+    def step_fused():
+        pd, sph = glue.project_and_render(depth)
+        return unet(glue.refine_input(pd, sph))
+
+    def timed(step):
+        with torch.no_grad():
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms_callers, ms_fused = timed(step_callers), timed(step_fused)
     return {"what": "GenRe 3D hot path (cam_bp + render_spherical + sph_bp + Unet_3D eval), batch %d, 2D nets excluded" % batch,
-            "ms_per_batch": ms, "shapes_per_s": batch / ms * 1e3}
+            "ms_per_batch": ms_fused, "shapes_per_s": batch / ms_fused * 1e3, "glue": "fused (genre_shapehd_b200/fused.py)",
+            "callers_glue_ms_per_batch": ms_callers, "callers_glue_shapes_per_s": batch / ms_callers * 1e3}
 
 
 def main():

@@ -47,6 +47,10 @@ _SIGNATURES = {
                                            _int, _ptr],
     "genre_b200_convt_c1_tc_forward": [_ptr, _int, _ptr, _int, _i64, _i64, _i64, _i64, _ptr, _int, _ptr, _int, _ptr, _ptr],
     "genre_b200_blocked_f32_to_f16": [_ptr, _int, _i64, _i64, _i64, _ptr, _ptr],
+    "genre_b200_render_spherical_forward_pre": [_ptr, _i64, _int, _ptr, _int, _int, _ptr, _f32, _f32, _f32, _ptr, _ptr],
+    "genre_b200_sph_bp_forward_fused": [_ptr] + [_i64] * 8 + [_ptr] + [_i64] * 5 + [_f32, _f32, _ptr, _i64, _int, _ptr,
+                                                                                       _size, _ptr],
+    "genre_b200_scale_clamp_strided": [_ptr, _i64, _i64, _f32, _f32, _f32, _ptr, _i64, _ptr],
     "genre_b200_ncdhw_to_blocked": [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _ptr, _ptr],
     "genre_b200_blocked_to_ncdhw": [_ptr, _int, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
     "genre_b200_cam_bp_stage_project": [_ptr] + [_i64] * 8 + [_ptr, _i64, _i64, _ptr, _i64, _i64, _int, _ptr, _size,
@@ -70,6 +74,7 @@ _LAUNCHES = {
     "genre_b200_cam_bp_stage_project": 1, "genre_b200_voxelize_stage_splat": 1,
     "genre_b200_convt3d_s2_forward": 1, "genre_b200_conv3d_taps_forward": 1,
     "genre_b200_convt_c1_forward": 1, "genre_b200_conv3d_k4s2_forward": 1,
+    "genre_b200_render_spherical_forward_pre": 1, "genre_b200_sph_bp_forward_fused": 2, "genre_b200_scale_clamp_strided": 1,
     "genre_b200_convt_c1_tc_forward": 1, "genre_b200_blocked_f32_to_f16": 1,
     "genre_b200_convt3d_s2_merged_forward": 1, "genre_b200_conv3d_k8s2_s4d_forward": 1, "genre_b200_ncdhw_to_blocked": 1, "genre_b200_blocked_to_ncdhw": 1,
 }

@@ -193,6 +193,21 @@ regroup_f16_kernel(const float4 *__restrict__ src, uint4 *__restrict__ dst, int 
   }
 }
 
+// dst[m][i] = clamp(src[m][i] * scale, lo, hi), dst maps dst_stride floats apart (a channel of a wider tensor)
+__global__ void __launch_bounds__(LY_THREADS)
+scale_clamp_kernel(const float4 *__restrict__ src, float *__restrict__ dst, size_t n4, size_t dst_stride, size_t total4,
+                   float scale, float lo, float hi) {
+  for (size_t i = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; i < total4; i += (size_t)gridDim.x * LY_THREADS) {
+    const size_t m = i / n4, j = i - m * n4;
+    float4 v = __ldg(src + i);
+    v.x = fminf(fmaxf(__fmul_rn(v.x, scale), lo), hi);
+    v.y = fminf(fmaxf(__fmul_rn(v.y, scale), lo), hi);
+    v.z = fminf(fmaxf(__fmul_rn(v.z, scale), lo), hi);
+    v.w = fminf(fmaxf(__fmul_rn(v.w, scale), lo), hi);
+    st_stream_f4(dst + m * dst_stride + j * 4, v);
+  }
+}
+
 static unsigned ly_grid(size_t n) {
   const size_t blocks = (n + LY_THREADS - 1) / LY_THREADS;
   const size_t cap = 148ull * 8 * 16;  // grid-stride beyond ~16 waves of 8 CTAs per SM
@@ -267,4 +282,17 @@ extern "C" int genre_b200_blocked_f32_to_f16(const float *src, int cg4, int64_t 
   regroup_f16_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, (uint4 *)dst, cg4, cg8, plane,
                                                                           units);
   return check_launch("regroup_f16 kernel");
+}
+
+// dst[m][:] = clamp(src[m][:] * scale, lo, hi) for `maps` maps of n floats, dst maps dst_map_stride floats apart:
+// GenRe's `clamp(proj_depth / 50, 1e-5, 1 - 1e-5)` + torch.cat (genre_full_model.py:126-127) as one pass.
+extern "C" int genre_b200_scale_clamp_strided(const float *src, int64_t maps, int64_t n, float scale, float lo, float hi,
+                                              float *dst, int64_t dst_map_stride, void *stream) {
+  GB_REQUIRE(src && dst && maps > 0 && n > 0 && n % 4 == 0 && dst_map_stride >= n && dst_map_stride % 4 == 0,
+             GENRE_B200_EINVAL, "scale_clamp: bad argument (n and stride must be multiples of 4)");
+  GB_REQUIRE(aligned16(src) && aligned16(dst), GENRE_B200_EALIGN, "scale_clamp: alignment");
+  const size_t n4 = (size_t)n / 4, total4 = n4 * (size_t)maps;
+  scale_clamp_kernel<<<ly_grid(total4), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, dst, n4,
+                                                                           (size_t)dst_map_stride, total4, scale, lo, hi);
+  return check_launch("scale_clamp kernel");
 }

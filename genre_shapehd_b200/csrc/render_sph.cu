@@ -54,15 +54,28 @@ __device__ __forceinline__ int tap_offset(int i, int R) {
   return ((i >> 2) & 1) * R * R + ((i >> 1) & 1) * R + (i & 1);
 }
 
-__device__ __forceinline__ float sample_trilinear(const float *__restrict__ vol, const Taps &t, int R) {
+// Optional transform of every voxel value as it is fetched: v -> clamp(v * scale, lo, hi).  GenRe renders
+// clamp(proj * 50, 1e-5, 1 - 1e-5) (depth_pred_with_sph_inpaint.py:124): applying the two elementwise ops here (same
+// fp32 operations, same order) removes two dense passes over the volume.  Out-of-volume taps stay 0 (zero padding).
+struct VoxPre {
+  float scale, lo, hi;
+};
+template <bool PRE>
+__device__ __forceinline__ float fetch_vox(const float *__restrict__ p, const VoxPre &pre) {
+  const float v = __ldg(p);
+  return PRE ? fminf(fmaxf(__fmul_rn(v, pre.scale), pre.lo), pre.hi) : v;
+}
+
+template <bool PRE>
+__device__ __forceinline__ float sample_trilinear(const float *__restrict__ vol, const Taps &t, int R, const VoxPre &pre) {
   float acc = 0.0f;
   if (t.valid == 0xFFu) {  // interior: 4 pairs of z-adjacent taps
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc = fmaf(__ldg(vol + t.base + tap_offset(i, R)), t.w[i], acc);
+    for (int i = 0; i < 8; ++i) acc = fmaf(fetch_vox<PRE>(vol + t.base + tap_offset(i, R), pre), t.w[i], acc);
   } else if (t.valid) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (t.valid & (1u << i)) acc = fmaf(__ldg(vol + t.base + tap_offset(i, R)), t.w[i], acc);
+      if (t.valid & (1u << i)) acc = fmaf(fetch_vox<PRE>(vol + t.base + tap_offset(i, R), pre), t.w[i], acc);
   }
   return acc;
 }
@@ -100,9 +113,10 @@ constexpr float RS_PMIN = 1e-5f;
 constexpr float RS_PMAX = (float)(1.0 - 1e-5);
 
 // forward pass over one ray; returns (sum_k s_k w_k, prod_k (1 - p_k)) to every lane
+template <bool PRE>
 __device__ __forceinline__ void render_ray(const float *__restrict__ vol, int R, double dx2, double dy2, double dz2,
-                                           int Z, const float *__restrict__ depth_weight, float &exp_depth,
-                                           float &trans) {
+                                           int Z, const float *__restrict__ depth_weight, const VoxPre &pre,
+                                           float &exp_depth, float &trans) {
   const int lane = threadIdx.x & 31;
   const double step = Z > 1 ? 1.0 / (double)(Z - 1) : 0.0;
   float carry = 1.0f, acc = 0.0f;
@@ -114,7 +128,7 @@ __device__ __forceinline__ void render_ray(const float *__restrict__ vol, int R,
       ray_point(dx2, dy2, dz2, k, Z, step, gx, gy, gz);
       Taps t;
       make_taps(gx, gy, gz, R, t);
-      p = fminf(fmaxf(sample_trilinear(vol, t, R), RS_PMIN), RS_PMAX);
+      p = fminf(fmaxf(sample_trilinear<PRE>(vol, t, R, pre), RS_PMIN), RS_PMAX);
     }
     float total;
     const float before = carry * warp_excl_prod32(1.0f - p, total);
@@ -126,9 +140,11 @@ __device__ __forceinline__ void render_ray(const float *__restrict__ vol, int R,
   trans = carry;
 }
 
+template <bool PRE>
 __global__ void __launch_bounds__(RS_THREADS)
 render_spherical_forward_kernel(const float *__restrict__ vox, int R, const double *__restrict__ dirs, int S, int Z,
-                                const float *__restrict__ depth_weight, float *__restrict__ out, long long n_rays) {
+                                const float *__restrict__ depth_weight, float *__restrict__ out, long long n_rays,
+                                const VoxPre pre) {
   const long long ray = (long long)blockIdx.x * (RS_THREADS / 32) + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
   const int pix = (int)(ray % ((long long)S * S));
@@ -136,7 +152,7 @@ render_spherical_forward_kernel(const float *__restrict__ vox, int R, const doub
   const float *vol = vox + (size_t)n * R * R * R;
   const double dx2 = dirs[pix * 3 + 0] * 2.0, dy2 = dirs[pix * 3 + 1] * 2.0, dz2 = dirs[pix * 3 + 2] * 2.0;
   float e, t;
-  render_ray(vol, R, dx2, dy2, dz2, Z, depth_weight, e, t);
+  render_ray<PRE>(vol, R, dx2, dy2, dz2, Z, depth_weight, pre, e, t);
   if ((threadIdx.x & 31) == 0) out[ray] = e + t;
 }
 
@@ -177,7 +193,7 @@ render_spherical_backward_kernel(const float *__restrict__ vox, int R, const dou
         ray_point(dx2, dy2, dz2, k, Z, step, gx, gy, gz);
         Taps t;
         make_taps(gx, gy, gz, R, t);
-        raw[c] = sample_trilinear(vol, t, R);
+        raw[c] = sample_trilinear<false>(vol, t, R, VoxPre{});
         p = fminf(fmaxf(raw[c], RS_PMIN), RS_PMAX);
       }
       float total;
@@ -242,9 +258,25 @@ extern "C" int genre_b200_render_spherical_forward(const float *vox, int64_t N, 
   GB_REQUIRE(out != nullptr, GENRE_B200_EINVAL, "render_spherical: out is null");
   const long long n_rays = (long long)N * sph_res * sph_res;
   const unsigned grid = (unsigned)((n_rays + RS_THREADS / 32 - 1) / (RS_THREADS / 32));
-  render_spherical_forward_kernel<<<grid, RS_THREADS, 0, as_stream(stream)>>>(vox, res, dirs, sph_res, z_res,
-                                                                              depth_weight, out, n_rays);
+  render_spherical_forward_kernel<false><<<grid, RS_THREADS, 0, as_stream(stream)>>>(vox, res, dirs, sph_res, z_res,
+                                                                                     depth_weight, out, n_rays, VoxPre{});
   return check_launch("render_spherical forward kernel");
+}
+
+// Same renderer over clamp(vox * pre_scale, pre_lo, pre_hi) without materialising that volume (forward only: the
+// fused GenRe inference path, depth_pred_with_sph_inpaint.py:124 `render_spherical(clamp(proj * 50, 1e-5, 1 - 1e-5))`).
+extern "C" int genre_b200_render_spherical_forward_pre(const float *vox, int64_t N, int res, const double *dirs,
+                                                       int sph_res, int z_res, const float *depth_weight,
+                                                       float pre_scale, float pre_lo, float pre_hi, float *out,
+                                                       void *stream) {
+  if (int rc = rs_check(vox, N, res, dirs, sph_res, z_res, depth_weight)) return rc;
+  GB_REQUIRE(out != nullptr, GENRE_B200_EINVAL, "render_spherical: out is null");
+  GB_REQUIRE(pre_lo <= pre_hi, GENRE_B200_EINVAL, "render_spherical: empty clamp range");
+  const long long n_rays = (long long)N * sph_res * sph_res;
+  const unsigned grid = (unsigned)((n_rays + RS_THREADS / 32 - 1) / (RS_THREADS / 32));
+  render_spherical_forward_kernel<true><<<grid, RS_THREADS, 0, as_stream(stream)>>>(
+      vox, res, dirs, sph_res, z_res, depth_weight, out, n_rays, VoxPre{pre_scale, pre_lo, pre_hi});
+  return check_launch("render_spherical forward kernel (pre-transform)");
 }
 
 extern "C" int genre_b200_render_spherical_backward(const float *vox, int64_t N, int res, const double *dirs,

@@ -31,11 +31,12 @@ __device__ __forceinline__ SphPoint sph_unproject(float r, float dxg, float dyg,
 
 constexpr int SPH_PIX = 4;  // pixels per thread in the project stage
 
-template <bool W_FAST>
+// AFFINE: the radius is in_bias + in_scale * map value (GenRe feeds 1 - cropped map, genre_full_model.py:139)
+template <bool W_FAST, bool AFFINE>
 __global__ void __launch_bounds__(SPH_THREADS)
 sph_project_kernel(const float *__restrict__ sph, int C, int H, int W, long long sN, long long sC, long long sH,
                    long long sW, const float *__restrict__ grid, long long gN, long long gC, long long gH,
-                   long long gW, long long gD, int R, float qscale, VoxWorkspace ws) {
+                   long long gW, long long gD, int R, float qscale, VoxWorkspace ws, float in_scale, float in_bias) {
   extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the splat grid start launching behind us
   const int map = blockIdx.y;
@@ -56,6 +57,7 @@ sph_project_kernel(const float *__restrict__ sph, int C, int H, int W, long long
     dxg[k] = dyg[k] = dzg[k] = 0.0f;
     if (p < P) {
       r[k] = smap[h * sH + w * sW];
+      if (AFFINE) r[k] = __fadd_rn(in_bias, __fmul_rn(in_scale, r[k]));
       const float *g = gmap + h * gH + w * gW;
       dxg[k] = g[0];
       dyg[k] = g[gD];
@@ -132,10 +134,11 @@ static int sph_check(const float *sph, int64_t N, int64_t C, int64_t H, int64_t 
 
 using namespace gb;
 
-extern "C" int genre_b200_sph_bp_forward(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN,
-                                         int64_t sC, int64_t sH, int64_t sW, const float *grid, int64_t gN, int64_t gC,
-                                         int64_t gH, int64_t gW, int64_t gD, float *tdf, float *cnt, int res,
-                                         void *workspace, size_t workspace_bytes, void *stream) {
+static int sph_forward_impl(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN, int64_t sC,
+                            int64_t sH, int64_t sW, const float *grid, int64_t gN, int64_t gC, int64_t gH, int64_t gW,
+                            int64_t gD, float *tdf, float *cnt, int res, void *workspace, size_t workspace_bytes,
+                            void *stream, bool affine, float in_scale, float in_bias, float alpha, float beta,
+                            int64_t out_stride) {
   if (int rc = sph_check(sph, N, C, H, W, grid, res)) return rc;
   GB_REQUIRE(tdf != nullptr, GENRE_B200_EINVAL, "sph_bp: tdf is null");
   VoxWorkspace w;
@@ -147,16 +150,42 @@ extern "C" int genre_b200_sph_bp_forward(const float *sph, int64_t N, int64_t C,
   if (int rc = vox_clear_counts(w, N * C, st)) return rc;
   dim3 grd((unsigned)((P + SPH_THREADS * SPH_PIX - 1) / (SPH_THREADS * SPH_PIX)), (unsigned)(N * C));
   const size_t smem = (size_t)w.ntiles * 4;
-  if (llabs(sW) <= llabs(sH))
-    sph_project_kernel<true><<<grd, SPH_THREADS, smem, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN, gC,
-                                                            gH, gW, gD, res, qscale, w);
-  else
-    sph_project_kernel<false><<<grd, SPH_THREADS, smem, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN,
-                                                             gC, gH, gW, gD, res, qscale, w);
+  const bool wf = llabs(sW) <= llabs(sH);
+#define GB_SPH(WF, AF)                                                                                              \
+  sph_project_kernel<WF, AF><<<grd, SPH_THREADS, smem, st>>>(sph, (int)C, (int)H, (int)W, sN, sC, sH, sW, grid, gN, gC, \
+                                                            gH, gW, gD, res, qscale, w, in_scale, in_bias)
+  if (wf && affine) GB_SPH(true, true);
+  else if (wf) GB_SPH(true, false);
+  else if (affine) GB_SPH(false, true);
+  else GB_SPH(false, false);
+#undef GB_SPH
   if (int rc = check_launch("sph_bp project kernel")) return rc;
+  return vox_splat(w, N * C, P, res, tdf, cnt, alpha, beta, 0.0f, st, true, out_stride);
+}
+
+extern "C" int genre_b200_sph_bp_forward(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN,
+                                         int64_t sC, int64_t sH, int64_t sW, const float *grid, int64_t gN, int64_t gC,
+                                         int64_t gH, int64_t gW, int64_t gD, float *tdf, float *cnt, int res,
+                                         void *workspace, size_t workspace_bytes, void *stream) {
   // tdf = mean distance on hit voxels, 0 elsewhere (sperical_to_tdf.py:26-27 zero init, kernel bias 0 at :695)
   const float beta = (float)((1.0 / 16777216.0) / (double)res);
-  return vox_splat(w, N * C, P, res, tdf, cnt, 0.0f, beta, 0.0f, st);
+  return sph_forward_impl(sph, N, C, H, W, sN, sC, sH, sW, grid, gN, gC, gH, gW, gD, tdf, cnt, res, workspace,
+                          workspace_bytes, stream, false, 1.0f, 0.0f, 0.0f, beta, 0);
+}
+
+// Fused form of GenRe's spherical back-projection glue (genre_full_model.py:134-143):
+//     radius = in_bias + in_scale * sph          (the caller's `1 - crop_sph`; the crop is just strides)
+//     out    = (-tdf + 1/R) * R * clamp(cnt,0,1) = 1 - R * mean distance on hit voxels, 0 elsewhere
+// written with a per-map stride of out_map_stride floats (>= R^3), i.e. straight into a channel of the refiner's
+// [B,2,R,R,R] input.  No count volume, no elementwise passes.  Inference only (no backward through this form).
+extern "C" int genre_b200_sph_bp_forward_fused(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN,
+                                               int64_t sC, int64_t sH, int64_t sW, const float *grid, int64_t gN,
+                                               int64_t gC, int64_t gH, int64_t gW, int64_t gD, float in_scale,
+                                               float in_bias, float *out, int64_t out_map_stride, int res,
+                                               void *workspace, size_t workspace_bytes, void *stream) {
+  GB_REQUIRE(out_map_stride >= (int64_t)res * res * res, GENRE_B200_EINVAL, "sph_bp fused: out_map_stride too small");
+  return sph_forward_impl(sph, N, C, H, W, sN, sC, sH, sW, grid, gN, gC, gH, gW, gD, out, nullptr, res, workspace,
+                          workspace_bytes, stream, true, in_scale, in_bias, 1.0f, -(1.0f / 16777216.0f), out_map_stride);
 }
 
 extern "C" int genre_b200_sph_bp_backward(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN,

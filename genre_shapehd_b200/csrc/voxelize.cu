@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(VOX_SPLAT_THREADS)
 vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ovf,
                  const unsigned *__restrict__ counts, const unsigned *__restrict__ ovf_count,
                  float *__restrict__ tdf, float *__restrict__ cnt, long long P, long long nvox, int ntiles,
-                 float alpha, float beta, float bg) {
+                 float alpha, float beta, float bg, long long out_stride) {
   __shared__ __align__(16) unsigned s_lo[VOX_TILE];
   __shared__ __align__(16) unsigned s_hi[VOX_TILE];
   const int tile = blockIdx.x, map = blockIdx.y, tid = threadIdx.x;
@@ -71,7 +71,7 @@ vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ov
   const unsigned n = counts[tix];
   const long long start = (long long)tile * VOX_TILE;
   const int nv = (int)min((long long)VOX_TILE, nvox - start);
-  float *out = tdf + (size_t)map * nvox + start;
+  float *out = tdf + (size_t)map * out_stride + start;  // out_stride > nvox: a channel of a wider tensor
   float *cout = WRITE_CNT ? cnt + (size_t)map * nvox + start : nullptr;
 
   if (n == 0) {  // background-only tile: pure streaming fill, no shared memory touched
@@ -153,7 +153,7 @@ vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ov
 
 template <bool VEC, bool WRITE_CNT>
 static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long long nvox, float *tdf, float *cnt,
-                        float alpha, float beta, float bg, cudaStream_t st, bool pdl) {
+                        float alpha, float beta, float bg, cudaStream_t st, bool pdl, long long out_stride) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)w.ntiles, (unsigned)n_maps);
   cfg.blockDim = dim3(VOX_SPLAT_THREADS);
@@ -169,7 +169,7 @@ static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long l
   const long long Pll = (long long)P;
   const int ntiles = w.ntiles;
   cudaError_t e = cudaLaunchKernelEx(&cfg, vox_splat_kernel<VEC, WRITE_CNT>, buckets, ovf, counts, ovf_count, tdf, cnt,
-                                     Pll, nvox, ntiles, alpha, beta, bg);
+                                     Pll, nvox, ntiles, alpha, beta, bg, out_stride);
   if (e != cudaSuccess) {
     set_error("voxelize splat kernel: %s", cudaGetErrorString(e));
     cudaGetLastError();
@@ -179,15 +179,16 @@ static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long l
 }
 
 int vox_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, int res, float *tdf, float *cnt, float alpha,
-              float beta, float bg, cudaStream_t st, bool pdl) {
+              float beta, float bg, cudaStream_t st, bool pdl, long long out_stride) {
   const long long nvox = (long long)res * res * res;
-  const bool vec = (nvox % 4 == 0) && aligned16(tdf) && (!cnt || aligned16(cnt));
+  if (out_stride <= 0) out_stride = nvox;
+  const bool vec = (nvox % 4 == 0) && (out_stride % 4 == 0) && aligned16(tdf) && (!cnt || aligned16(cnt));
   if (vec) {
-    return cnt ? launch_splat<true, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl)
-               : launch_splat<true, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl);
+    return cnt ? launch_splat<true, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl, out_stride)
+               : launch_splat<true, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl, out_stride);
   }
-  return cnt ? launch_splat<false, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl)
-             : launch_splat<false, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl);
+  return cnt ? launch_splat<false, true>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl, out_stride)
+             : launch_splat<false, false>(w, n_maps, P, nvox, tdf, cnt, alpha, beta, bg, st, pdl, out_stride);
 }
 
 // arguments shared by both back-projections

@@ -257,6 +257,31 @@ int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t 
 int genre_b200_blocked_to_ncdhw(const float *src, int cg, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
                                 float *dst, void *stream);
 
+/* ---- fused GenRe glue (opt-in, inference only; genre_shapehd_b200/fused.py) --------------------------
+ * The frozen callers wrap the ops in ~19 dense elementwise passes over 128^3 volumes (depth_pred_with_sph_inpaint.py:
+ * 120-126, genre_full_model.py:120-143).  These three entry points fold them into the kernels. */
+
+/* render_spherical over clamp(vox * pre_scale, pre_lo, pre_hi) applied as each voxel is fetched
+ * (`render_spherical(torch.clamp(proj * 50, 1e-5, 1 - 1e-5))`, depth_pred_with_sph_inpaint.py:124). */
+int genre_b200_render_spherical_forward_pre(const float *vox, int64_t N, int res, const double *dirs,
+                                            int sph_res, int z_res, const float *depth_weight,
+                                            float pre_scale, float pre_lo, float pre_hi, float *out, void *stream);
+
+/* Net.backproject_spherical (genre_full_model.py:134-143) in one call: radius = in_bias + in_scale * sph (the
+ * `1 - crop_sph`; the crop is expressed through the strides), out = 1 - R * mean distance on hit voxels and 0
+ * elsewhere (= (-tdf + 1/R) * R * clamp(cnt,0,1)), maps written out_map_stride floats apart (a channel of the
+ * refiner's [B,2,R,R,R] input).  Workspace as genre_b200_sph_bp_forward. */
+int genre_b200_sph_bp_forward_fused(const float *sph, int64_t N, int64_t C, int64_t H, int64_t W,
+                                    int64_t sN, int64_t sC, int64_t sH, int64_t sW,
+                                    const float *grid, int64_t gN, int64_t gC, int64_t gH, int64_t gW, int64_t gD,
+                                    float in_scale, float in_bias, float *out, int64_t out_map_stride, int res,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* dst[m][:] = clamp(src[m][:] * scale, lo, hi), dst maps dst_map_stride floats apart
+ * (`torch.clamp(proj_depth / 50, 1e-5, 1 - 1e-5)` + torch.cat, genre_full_model.py:126-127). */
+int genre_b200_scale_clamp_strided(const float *src, int64_t maps, int64_t n, float scale, float lo, float hi,
+                                   float *dst, int64_t dst_map_stride, void *stream);
+
 /* blocked fp32 [BD][cg4][H][W][4] -> blocked fp16 [BD][(cg4+1)/2][H][W][8], channel padding zero-filled: turns the
  * fp32 output of one tensor-core layer into the fp16 operand of the next without going through NCDHW */
 int genre_b200_blocked_f32_to_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst, void *stream);

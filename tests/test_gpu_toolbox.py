@@ -375,6 +375,36 @@ def test_render_spherical_backward_vs_autograd_of_the_composition():
     assert (a.grad - b.grad).abs().max().item() <= 2e-4 * scale
 
 
+@pytest.mark.parametrize("batch", [1, 3])
+def test_fused_genre_glue_matches_the_callers_op_by_op_lines(oracle, batch):
+    """genre_shapehd_b200/fused.py against the frozen callers' glue (depth_pred_with_sph_inpaint.py:120-126,
+    genre_full_model.py:120-143) run on the drop-in ops; differences are rounding only"""
+    from genre_shapehd_b200.fused import GenRe3DGlue
+    from genre_shapehd_b200.synth import bench_depth_batch
+    glue = GenRe3DGlue().to(DEV)
+    depth = dev(bench_depth_batch(batch))
+    with torch.no_grad():
+        proj, sph_in = glue.project_and_render(depth)
+        # the callers' lines
+        proj_ref = Camera_back_projection_layer()(depth)
+        sph_ref = sph_pad(glue.render(torch.clamp(proj_ref * 50, 1e-5, 1 - 1e-5)), 16)
+        assert torch.equal(proj, proj_ref)
+        assert (sph_in - sph_ref).abs().max().item() <= 1e-6
+        # a stand-in for the inpainting net's output: the padded partial map, perturbed
+        g = torch.Generator(device=DEV).manual_seed(3)
+        pred_sph = (sph_ref + 0.01 * torch.rand(sph_ref.shape, device=DEV, generator=g)).clamp(0, 1)
+        refine = glue.refine_input(proj, pred_sph)
+        grid = glue.grid.expand(batch, -1, -1, -1, -1)
+        crop = pred_sph[:, :, 16:144, 16:144]
+        df, cnt = SphericalBackProjection.apply(1 - crop, grid, 128)
+        ps = (-df + 1 / 128) * 128 * torch.clamp(cnt, 0, 1)
+        pd = torch.clamp((proj_ref * 50) / 50, 1e-5, 1 - 1e-5)
+        ref = torch.cat((ps, pd), dim=1)
+    assert refine.shape == ref.shape
+    assert torch.equal(refine[:, 0] != 0, ps[:, 0] != 0)                      # same hit voxels
+    assert (refine - ref).abs().max().item() <= 1e-5
+
+
 def test_sph_pad_and_grid_buffers_match_reference_layout():
     m = render_spherical()
     assert tuple(m.grid.shape) == (128, 128, 256, 3) and tuple(m.depth_weight.shape) == (256,)
