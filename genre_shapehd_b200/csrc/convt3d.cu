@@ -238,7 +238,7 @@ convt3d_s2_kernel(const ConvTParams p) {
     tz = q / nchunk;
     kc = q - tz * nchunk;
     if (p.srcpar_cgs) {
-      const int sv = (kc * CT_KCG) / p.srcpar_cgs;
+      const int sv = ((kc * CT_KCG) / p.srcpar_cgs) & 7;  // & 7: the K range may hold several blocks of 8 sub-volumes (3xTF32)
       bz = 1 - ((sv >> 2) & 1);
       by = 1 - ((sv >> 1) & 1);
       bx = 1 - (sv & 1);
@@ -698,10 +698,11 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
 // enc2..enc5 :152-155) on the same kernel: the input arrives as its 8 parity sub-volumes in ONE channel-blocked tensor
 //   src [B*D'][8*cgs][H'][W'][16 B]   (D' = D/2 ...; channel group index = s*cgs + c, s = (pz*2+py)*2+px)
 // and sub-volume s is a K range with 2 taps per dimension: in[2(o+delta)+p] with delta = (1-p) - t, k = 3 - 2t - p.
-//   wpack [2 z-tap][8*cgs/2 chunk][4 taps][2][npad/8][8][g];  out [B*D'][cgo][H'][W'][4] fp32
+//   wpack [2 z-tap][kblocks*8*cgs/2 chunk][4 taps][2][npad/8][8][g];  out [B*D'][cgo][H'][W'][4] fp32
+//   kblocks (1, or 3 for the hi|lo|hi operand of the 3xTF32 mode): how many such 8-sub-volume blocks the K range holds
 // Supported: W' in {16, 32}, H' % 16 == 0, cgs even, npad in {32, 64, 96, 128}.
-extern "C" int genre_b200_conv3d_k4s2_forward(const void *src_, int cgs, int64_t B, int64_t D, int64_t H, int64_t W,
-                                              const void *wpack_, int npad, int f16, const float *scale,
+extern "C" int genre_b200_conv3d_k4s2_forward(const void *src_, int cgs, int kblocks, int64_t B, int64_t D, int64_t H,
+                                              int64_t W, const void *wpack_, int npad, int f16, const float *scale,
                                               const float *shift, float slope, float *out, int cgo, void *stream) {
   const float *src = (const float *)src_, *wpack = (const float *)wpack_;
   g_conv_f16 = f16 != 0;
@@ -714,7 +715,7 @@ extern "C" int genre_b200_conv3d_k4s2_forward(const void *src_, int cgs, int64_t
   GB_REQUIRE(B * D * (H / CT_BY) < (1ll << 31), GENRE_B200_EINVAL, "conv3d_k4s2: grid too large");
   GB_REQUIRE(aligned16(src) && aligned16(wpack) && aligned16(out), GENRE_B200_EALIGN, "conv3d_k4s2: alignment");
   ConvTParams p;
-  p.src0 = src; p.src1 = nullptr; p.cg0 = 8 * cgs; p.cg1 = 0;
+  p.src0 = src; p.src1 = nullptr; p.cg0 = 8 * cgs * (kblocks > 0 ? kblocks : 1); p.cg1 = 0;
   p.B = (int)B; p.D = (int)D; p.H = (int)H; p.W = (int)W;
   p.wpack = wpack; p.scale = scale; p.shift = shift; p.slope = slope; p.out = out; p.cgo = cgo;
   p.srcpar_cgs = cgs;

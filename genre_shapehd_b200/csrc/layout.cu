@@ -208,6 +208,30 @@ scale_clamp_kernel(const float4 *__restrict__ src, float *__restrict__ dst, size
   }
 }
 
+// fp32 -> (lo, hi, hi) for the 3xTF32 scheme: hi = x rounded to TF32 (10-bit mantissa), lo = x - hi (exact in fp32).
+// [BD][CG][H][W][4] -> [BD][3*CG][H][W][4] with the three blocks of CG groups in that order (weights: W_hi | W_lo | W_hi).
+__device__ __forceinline__ float tf32_round(float x) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(LY_THREADS)
+split3_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, int CG, size_t plane, size_t units) {
+  for (size_t u = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; u < units; u += (size_t)gridDim.x * LY_THREADS) {
+    const size_t hw = u % plane;
+    size_t r = u / plane;
+    const int cg = (int)(r % CG);
+    r /= CG;  // b * D + d
+    const float4 v = __ldg(src + u);
+    const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+    const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    float4 *o = dst + (r * 3 * CG + cg) * plane + hw;
+    o[0] = lo;  // small terms first: the tensor core's fp32 accumulator truncates, so the error of a step scales with
+    o[(size_t)CG * plane] = hi;  // the partial sum it is added to; the two cross terms go in while that sum is ~2^-11 of
+    o[(size_t)2 * CG * plane] = hi;  // its final size
+  }
+}
+
 static unsigned ly_grid(size_t n) {
   const size_t blocks = (n + LY_THREADS - 1) / LY_THREADS;
   const size_t cap = 148ull * 8 * 16;  // grid-stride beyond ~16 waves of 8 CTAs per SM
@@ -295,4 +319,15 @@ extern "C" int genre_b200_scale_clamp_strided(const float *src, int64_t maps, in
   scale_clamp_kernel<<<ly_grid(total4), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, dst, n4,
                                                                            (size_t)dst_map_stride, total4, scale, lo, hi);
   return check_launch("scale_clamp kernel");
+}
+
+// blocked fp32 [BD][cg][H][W][4] -> [BD][3*cg][H][W][4] = (lo | hi | hi) blocks, hi = TF32-rounded value, lo = the
+// remainder: the activation operand of the fp32-accurate "3xTF32" convolution mode (A_lo*W_hi + A_hi*W_lo + A_hi*W_hi)
+extern "C" int genre_b200_blocked_split3(const float *src, int cg, int64_t BD, int64_t H, int64_t W, float *dst,
+                                         void *stream) {
+  GB_REQUIRE(src && dst && cg > 0 && BD > 0 && H > 0 && W > 0, GENRE_B200_EINVAL, "blocked_split3: bad argument");
+  GB_REQUIRE(aligned16(src) && aligned16(dst), GENRE_B200_EALIGN, "blocked_split3: alignment");
+  const size_t plane = (size_t)(H * W), units = (size_t)BD * cg * plane;
+  split3_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, (float4 *)dst, cg, plane, units);
+  return check_launch("split3 kernel");
 }

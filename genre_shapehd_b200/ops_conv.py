@@ -48,8 +48,62 @@ MERGE_PARITIES = os.environ.get("GENRE_B200_CONV_MERGE", "1") != "0"
 S4D_SPLIT_Z = os.environ.get("GENRE_B200_S4D_SPLIT_Z", "0") != "0"   # measured: 0.88 vs 0.80 ms, so off
 
 
+# With torch.backends.cudnn.allow_tf32 off the caller asks for fp32 convolutions: the kernels then run the 3xTF32 scheme
+# (operands split into TF32 hi + lo parts, A_lo*W_hi + A_hi*W_lo + A_hi*W_hi accumulated in fp32: ~1e-5 relative error, set by the accumulator's truncation,
+# 3x the MMAs of the TF32 mode) so that occupancies match the fp32 reference within 1e-4.  "0": fall back to cuDNN fp32.
+EXACT_WHEN_TF32_OFF = os.environ.get("GENRE_B200_CONV_EXACT", "1") != "0"
+
+
+def _mode():
+    """operand mode of the next launch: 'f16' | 'tf32' (single pass, 10-bit operand mantissa = what cuDNN itself does
+    while torch.backends.cudnn.allow_tf32 is on) or 'fp32x3' (fp32-accurate) when it is off or asked for explicitly"""
+    if not torch.backends.cudnn.allow_tf32:
+        return "fp32x3"
+    return PRECISION
+
+
 def _f16():
-    return PRECISION == "f16"
+    return _mode() == "f16"
+
+
+def _x3():
+    return _mode() == "fp32x3"
+
+
+def _tf32_hi(w):
+    """w rounded to TF32 (nearest, ties away - cvt.rna.tf32.f32) but kept in fp32 storage"""
+    i = w.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _split3(t):
+    """blocked fp32 [BD,CG,H,W,4] -> [BD,3CG,H,W,4] = (lo | hi | hi) blocks (csrc/layout.cu split3_kernel)"""
+    bd, cg, h, w, _ = t.shape
+    out = torch.empty((bd, 3 * cg, h, w, 4), device=t.device, dtype=torch.float32)
+    _lib.call("genre_b200_blocked_split3", t.data_ptr(), cg, bd, h, w, out.data_ptr(), _lib.stream_ptr(t))
+    return out
+
+
+def _x3_operands(src0, src1):
+    """in fp32x3 mode the (possibly two-source) K range becomes ONE tensor of lo | hi | hi blocks"""
+    if not _x3():
+        return src0, src1
+    t = src0 if src1 is None else torch.cat((src0, src1), dim=1)
+    return _split3(t.contiguous()), None
+
+
+def _pack(module, key, make, chunk_dim):
+    """packed weights of `module` for the current mode; fp32x3: (W_hi | W_lo | W_hi) along the K-chunk axis, matching the
+    (lo | hi | hi) activation blocks: the two small cross terms are accumulated first (the tensor core's fp32 accumulator
+    truncates, so a step's error scales with the partial sum it is added to)"""
+    if not _x3():
+        return _cached_pack(module, key, make)
+
+    def make3(w):
+        hi = _tf32_hi(w)
+        p_hi, p_lo = make(hi), make(w - hi)
+        return torch.cat((p_hi, p_lo, p_hi), dim=chunk_dim).contiguous()
+    return _cached_pack(module, key + ("x3",), make3)
 
 
 def _group():
@@ -241,6 +295,7 @@ def _convt_supported(shape_bcdhw, module):
 def convt3d_s2_blocked(src0, src1, batch, module, bn=None, slope=1.0):
     """Run the kernel on blocked operands (fp32 groups of 4 or fp16 groups of 8, matching PRECISION); returns the
     blocked fp32 output [B*2D, cgo, 2H, 2W, 4], or None when `bn` needs batch statistics."""
+    src0, src1 = _x3_operands(src0, src1)
     bd, cg0, h, w, _ = src0.shape
     cg1 = src1.shape[1] if src1 is not None else 0
     cout = module.out_channels
@@ -255,12 +310,12 @@ def convt3d_s2_blocked(src0, src1, batch, module, bn=None, slope=1.0):
     out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=dev, dtype=torch.float32)
     if merged:
         # the four (y,x) parity classes share one MMA stream: N = 4 x 20 columns (csrc/convt3d.cu MODE 2)
-        wpack = _cached_pack(module, ("convt_merged", 20, g), lambda wt: pack_convt_merged_weights(wt, 20, g))
+        wpack = _pack(module, ("convt_merged", 20, g), lambda wt: pack_convt_merged_weights(wt, 20, g), 2)
         _lib.call("genre_b200_convt3d_s2_merged_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
                   cg1, batch, bd // batch, h, w, wpack.data_ptr(), 8, 80, 1 if g == 8 else 0, aff[0].data_ptr(),
                   aff[1].data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
         return out
-    wpack = _cached_pack(module, ("convt", npad, g), lambda wt: pack_convt_weights(wt, npad, g))
+    wpack = _pack(module, ("convt", npad, g), lambda wt: pack_convt_weights(wt, npad, g), 4)
     _lib.call("genre_b200_convt3d_s2_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None, cg1,
               batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, 1 if g == 8 else 0,
               aff[0].data_ptr(), aff[1].data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
@@ -268,9 +323,9 @@ def convt3d_s2_blocked(src0, src1, batch, module, bn=None, slope=1.0):
 
 
 def _no_autograd(*tensors):
-    """The kernels are forward-only and compute in TF32: they run when no gradient is needed and TF32 convolutions
-    are allowed (torch.backends.cudnn.allow_tf32, PyTorch's own switch and default for the cuDNN path they replace)."""
-    if not torch.backends.cudnn.allow_tf32:
+    """The kernels are forward-only: they run when no gradient is needed.  torch.backends.cudnn.allow_tf32 (PyTorch's own
+    switch, on by default, for the cuDNN path they replace) selects the operand mode, see _mode()."""
+    if not torch.backends.cudnn.allow_tf32 and not EXACT_WHEN_TF32_OFF:
         return False
     return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
@@ -366,7 +421,7 @@ def pack_conv_k8s2_weights(weight, npad, group=4):
 
 def _packed_conv(module, npad):
     g = _group()
-    return _cached_pack(module, ("k8s2", npad, g), lambda w: pack_conv_k8s2_weights(w, npad, g))
+    return _pack(module, ("k8s2", npad, g), lambda w: pack_conv_k8s2_weights(w, npad, g), 1)
 
 
 def _conv_k8s2_supported(x, m):
@@ -459,13 +514,15 @@ def _conv_k4s2(x, m, bn, slope):
     g = _group()
     cin = x.shape[1]
     cpad = (cin + 2 * g - 1) // (2 * g) * (2 * g)      # a K chunk (2 channel groups) must not straddle sub-volumes
-    wpack = _cached_pack(m, ("k4s2", cpad, npad, g), lambda w: pack_conv_k4s2_weights(w, cpad, npad, g))
+    wpack = _pack(m, ("k4s2", cpad, npad, g), lambda w: pack_conv_k4s2_weights(w, cpad, npad, g), 1)
     xb = space_to_depth_sources(x, cpad, g, torch.float16 if _f16() else None)
+    if _x3():
+        xb = _split3(xb)
     b = x.shape[0]
     bd, _, h, wd, _ = xb.shape
     cgo = (cout + 3) // 4
     out = torch.empty((bd, cgo, h, wd, 4), device=x.device, dtype=torch.float32)
-    _lib.call("genre_b200_conv3d_k4s2_forward", xb.data_ptr(), cpad // g, b, bd // b, h, wd, wpack.data_ptr(), npad,
+    _lib.call("genre_b200_conv3d_k4s2_forward", xb.data_ptr(), cpad // g, 3 if _x3() else 1, b, bd // b, h, wd, wpack.data_ptr(), npad,
               1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
               out.data_ptr(), cgo, _lib.stream_ptr(x))
     return from_blocked(out, b, cout)
@@ -486,8 +543,11 @@ def conv3d(x, m, bn=None, slope=None):
         if aff is None:
             return None
         g, b, cout = _group(), x.shape[0], m.out_channels
-        wpack = _cached_pack(m, ("k8s2_s4d", 20, g, S4D_SPLIT_Z), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g, S4D_SPLIT_Z))
+        wpack = _pack(m, ("k8s2_s4d", 20, g, S4D_SPLIT_Z), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g, S4D_SPLIT_Z),
+                      2 if S4D_SPLIT_Z else 1)
         xb = space_to_depth4_blocked(x, g, torch.float16 if _f16() else None)
+        if _x3():
+            xb = _split3(xb)
         bd, cg, h, w, _ = xb.shape
         cgo = (cout + 3) // 4
         out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=x.device, dtype=torch.float32)
@@ -502,6 +562,8 @@ def conv3d(x, m, bn=None, slope=None):
     sc, sh = aff
     dev = x.device
     xb = space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x)
+    if _x3():
+        xb = _split3(xb)
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
     cgo = (cout + 3) // 4
@@ -533,6 +595,8 @@ def convt_c1_tc(inputs, m, sigmoid=False):
     """ConvTranspose3d(Cin -> 1, k4, s2, p1) over the channel concatenation of `inputs` on the tensor cores (MODE 4);
     NCDHW [B,1,2D,2H,2W] or None if not covered."""
     x0 = inputs[0]
+    if _x3():
+        return None   # fp32 wanted: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and cheaper than 3x the TF32 MMAs
     if not ("convt_c1_tc" in POLICY and ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
             and tuple(m.padding) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1)
             and m.groups == 1 and m.out_channels == 1 and len(inputs) <= 2

@@ -202,9 +202,9 @@ int genre_b200_conv3d_taps_forward(const void *src0, int cg0, const void *src1, 
  * (VoxelDiscriminator, networks/networks.py:247-250) and Unet_3D.enc2..enc5 (:152-155).  The input arrives as its 8 parity
  * sub-volumes in one channel-blocked tensor src [B*D'][8*cgs][H'][W'][16 B] (D' = D/2 ...; group index = s*cgs + c,
  * s = (pz*2+py)*2+px); sub-volume s is a K range with 2 taps per dimension (kernel index 3 - 2t - p).
- *   wpack [2][8*cgs/2][4][2][npad/8][8][g];  out [B*D'][cgo][H'][W'][4];  W' in {16,32}, H' % 16 == 0, cgs even,
- *   npad in {32,64,96,128}. */
-int genre_b200_conv3d_k4s2_forward(const void *src, int cgs, int64_t B, int64_t D, int64_t H, int64_t W,
+ *   wpack [2][kblocks*8*cgs/2][4][2][npad/8][8][g];  out [B*D'][cgo][H'][W'][4];  W' in {16,32}, H' % 16 == 0, cgs even,
+ *   npad in {32,64,96,128}.  kblocks: 1, or 3 when src holds the lo|hi|hi blocks of genre_b200_blocked_split3. */
+int genre_b200_conv3d_k4s2_forward(const void *src, int cgs, int kblocks, int64_t B, int64_t D, int64_t H, int64_t W,
                                    const void *wpack, int npad, int f16,
                                    const float *scale, const float *shift, float slope,
                                    float *out, int cgo, void *stream);
@@ -285,6 +285,13 @@ int genre_b200_scale_clamp_strided(const float *src, int64_t maps, int64_t n, fl
 /* blocked fp32 [BD][cg4][H][W][4] -> blocked fp16 [BD][(cg4+1)/2][H][W][8], channel padding zero-filled: turns the
  * fp32 output of one tensor-core layer into the fp16 operand of the next without going through NCDHW */
 int genre_b200_blocked_f32_to_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst, void *stream);
+
+/* blocked fp32 [BD][cg][H][W][4] -> [BD][3*cg][H][W][4] = (lo | hi | hi): hi = value rounded to TF32, lo = value - hi.
+ * With weights packed as (W_hi | W_lo | W_hi) along K, the TF32 tensor-core kernels above compute
+ * A_lo*W_hi + A_hi*W_lo + A_hi*W_hi = the fp32 product to ~2^-21 relative (small terms first: the tensor core's
+ * fp32 accumulator truncates, ~2^-26 of the partial sum per MMA step) ("3xTF32"): the mode the 3D nets run in when
+ * torch.backends.cudnn.allow_tf32 is off, so that occupancies match the fp32 reference within 1e-4. */
+int genre_b200_blocked_split3(const float *src, int cg, int64_t BD, int64_t H, int64_t W, float *dst, void *stream);
 
 #ifdef __cplusplus
 }

@@ -88,4 +88,14 @@ with torch.no_grad():
     out["unet3d_eval_cudnn_tf32_ms"] = timeit(lambda: net(x), reps=5, warm=2)
     torch.backends.cudnn.allow_tf32 = False
     out["unet3d_eval_cudnn_fp32_ms"] = timeit(lambda: net(x), reps=5, warm=2)
+    ops_conv.ENABLED = True     # allow_tf32 still off: the custom kernels run their fp32-accurate 3xTF32 mode
+    out["unet3d_eval_custom_fp32x3_ms"] = timeit(lambda: net(x), reps=5, warm=2)
+    for nm, cls in (("voxeldecoder", nets.VoxelDecoder),):
+        net_ = cls().to(dev).eval()
+        z = torch.randn(B, 200, device=dev)
+        out[nm + "_custom_fp32x3_ms"] = timeit(lambda: net_(z), reps=5, warm=2)
+        ops_conv.ENABLED = False
+        out[nm + "_cudnn_fp32_ms"] = timeit(lambda: net_(z), reps=5, warm=2)
+        ops_conv.ENABLED = True
+    torch.backends.cudnn.allow_tf32 = True
 print(json.dumps(out))

@@ -6,13 +6,36 @@ import torch.nn.functional as F
 from genre_shapehd_b200 import ops_conv
 import networks.networks as nets
 
+from contextlib import contextmanager
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(autouse=True, params=["f16", "tf32"])
+@contextmanager
+def fp32_reference():
+    """plain torch / cuDNN fp32 convolutions: custom kernels off, TF32 off"""
+    old = ops_conv.ENABLED
+    ops_conv.ENABLED = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        yield
+    finally:
+        ops_conv.ENABLED = old
+        torch.backends.cudnn.allow_tf32 = True
+
+
+def _tol():
+    """max |err| / max |ref| allowed for one layer: 10-bit operand mantissa for the single-pass modes (fp32 accumulate);
+    1e-4 for the 3xTF32 mode (north_star: values within 1e-4).  Measured for 3xTF32: 1e-6 .. 4e-5, growing with the number
+    of MMA steps per output (3000 for Unet_3D.dec5) because the tensor core's fp32 accumulator truncates (~2^-25 of the
+    partial sum per step); the operand split itself is good to 2^-21."""
+    return 1e-4 if ops_conv.PRECISION == "fp32x3" else 4e-3
+
+
+@pytest.fixture(autouse=True, params=["f16", "tf32", "fp32x3"])
 def _precision(request):
-    """every test runs with both operand types of the tensor-core kernels"""
+    """every test runs with the three operand modes of the tensor-core kernels"""
     torch.backends.cudnn.allow_tf32 = True   # the custom kernels decline when reduced-mantissa convolutions are disallowed
     old, oldp = ops_conv.PRECISION, set(ops_conv.POLICY)
     ops_conv.PRECISION = request.param
@@ -43,7 +66,7 @@ def test_convt3d_vs_torch(k, cin, cout, b, d, h, w):
     assert y.shape == ref.shape
     err = (y - ref).abs().max().item()
     scale = ref.abs().max().item()
-    assert err <= 4e-3 * scale, "max err %g vs scale %g" % (err, scale)   # TF32 operands (10-bit mantissa)
+    assert err <= _tol() * scale, "max err %g vs scale %g" % (err, scale)   # TF32 operands (10-bit mantissa)
 
 
 @pytest.mark.parametrize("cin,cout,b,d,h,w", [(16, 20, 1, 2, 16, 16), (80, 20, 2, 3, 32, 32), (32, 7, 1, 1, 16, 32)])
@@ -64,7 +87,7 @@ def test_convt_k8_merged_parities_vs_separate_and_torch(cin, cout, b, d, h, w):
         ops_conv.MERGE_PARITIES = old
     assert ym is not None and ys is not None
     scale = ref.abs().max().item()
-    assert (ym - ref).abs().max().item() <= 4e-3 * scale
+    assert (ym - ref).abs().max().item() <= _tol() * scale
     # same products, same fp32 accumulator; only the order of the K walk differs
     assert (ym - ys).abs().max().item() <= 1e-4 * scale
 
@@ -106,10 +129,9 @@ def test_deconv_skip_fused_bn_leaky_vs_torch():
     x, s = torch.randn(1, 40, 2, 32, 32, device=DEV), torch.randn(1, 40, 2, 32, 32, device=DEV)
     with torch.no_grad():
         y = blk(x, s)
-        torch.backends.cudnn.allow_tf32 = False
-        ref = blk.net(torch.cat((x, s), 1))
-        torch.backends.cudnn.allow_tf32 = True
-    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+        with fp32_reference():
+            ref = blk.net(torch.cat((x, s), 1))
+    assert (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
 
 
 def test_autograd_and_unsupported_shapes_fall_back():
@@ -132,11 +154,10 @@ def test_conv3d_k8s2_via_space_to_depth_vs_torch(cin, cout, b, d, h, w):
     with torch.no_grad():
         y = ops_conv.conv3d(x, m)
         assert y is not None
-        torch.backends.cudnn.allow_tf32 = False
-        ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=3)
-        torch.backends.cudnn.allow_tf32 = True
+        with fp32_reference():
+            ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=3)
     assert y.shape == ref.shape
-    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    assert (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("split_z", [True, False])
@@ -150,12 +171,11 @@ def test_conv3d_k8s2_s4d_both_class_layouts(split_z):
         ops_conv.S4D_SPLIT_Z = split_z
         with torch.no_grad():
             y = ops_conv.conv3d(x, m)
-            torch.backends.cudnn.allow_tf32 = False
-            ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=3)
-            torch.backends.cudnn.allow_tf32 = True
+            with fp32_reference():
+                ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=3)
     finally:
         ops_conv.S4D_SPLIT_Z = old
-    assert y is not None and (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    assert y is not None and (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
 
 
 def test_conv_block_fused_bn_leaky_vs_torch():
@@ -166,20 +186,29 @@ def test_conv_block_fused_bn_leaky_vs_torch():
     x = torch.rand(1, 2, 8, 64, 64, device=DEV)
     with torch.no_grad():
         y = blk(x)
-        torch.backends.cudnn.allow_tf32 = False
-        ref = blk.net(x)
-        torch.backends.cudnn.allow_tf32 = True
-    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+        with fp32_reference():
+            ref = blk.net(x)
+    assert (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
 
 
-def test_tf32_switch_is_honoured():
-    m = nets.ConvTranspose3d(16, 4, 4, 2, 1).to(DEV)
-    x = torch.randn(1, 16, 2, 16, 16, device=DEV)
+def test_tf32_switch_selects_the_fp32_accurate_mode(monkeypatch):
+    """torch.backends.cudnn.allow_tf32 = False asks for fp32 convolutions: the kernels answer with the 3xTF32 scheme
+    (fp32-grade accuracy), or hand the layer back to cuDNN when GENRE_B200_CONV_EXACT=0"""
+    torch.manual_seed(2)
+    m = nets.ConvTranspose3d(32, 8, 4, 2, 1).to(DEV)
+    x = torch.randn(1, 32, 2, 16, 16, device=DEV)
     with torch.no_grad():
+        with fp32_reference():
+            ref = F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=1)
         torch.backends.cudnn.allow_tf32 = False
-        assert ops_conv.conv_transpose3d(x, m) is None     # fp32 requested: the cuDNN fp32 path runs instead
-        torch.backends.cudnn.allow_tf32 = True
-        assert ops_conv.conv_transpose3d(x, m) is not None
+        try:
+            assert ops_conv._mode() == "fp32x3"
+            y = ops_conv.conv_transpose3d(x, m)
+            monkeypatch.setattr(ops_conv, "EXACT_WHEN_TF32_OFF", False)
+            assert ops_conv.conv_transpose3d(x, m) is None
+        finally:
+            torch.backends.cudnn.allow_tf32 = True
+    assert y is not None and (y - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("cin,b,d,h,w", [(8, 1, 3, 8, 8), (40, 2, 4, 16, 32), (32, 1, 5, 12, 20)])
@@ -191,9 +220,8 @@ def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
     with torch.no_grad():
         y = ops_conv.conv_transpose3d(x, m)
         assert y is not None
-        torch.backends.cudnn.allow_tf32 = False
-        ref = F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=1)
-        torch.backends.cudnn.allow_tf32 = True
+        with fp32_reference():
+            ref = F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=1)
     assert y.shape == ref.shape
     assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())   # plain fp32 FMAs
 
@@ -203,6 +231,8 @@ def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
 def test_convt_c1_tensor_core_vs_torch(chans, b, d, h, w, sigmoid):
     """MODE 4: ConvT(Cin -> 1) as 27 union taps x 8 output classes on the tensor cores; one or two (skip) sources, the
     20-channel ones arriving as blocked twins of a previous custom layer (zero-padded to the operand group size)"""
+    if ops_conv.PRECISION == "fp32x3":
+        pytest.skip("fp32 wanted: the 1-channel layer goes to the exact FP32-pipe kernel instead (test_dec6_two_source_path)")
     torch.manual_seed(sum(chans) + w)
     m = nets.ConvTranspose3d(sum(chans), 1, 4, 2, 1).to(DEV)
     xs = []
@@ -214,13 +244,12 @@ def test_convt_c1_tensor_core_vs_torch(chans, b, d, h, w, sigmoid):
     with torch.no_grad():
         y = ops_conv.convt_c1_tc(tuple(xs), m, sigmoid)
         assert y is not None
-        torch.backends.cudnn.allow_tf32 = False
-        ref = F.conv_transpose3d(torch.cat(xs, 1), m.weight, m.bias, stride=2, padding=1)
-        torch.backends.cudnn.allow_tf32 = True
+        with fp32_reference():
+            ref = F.conv_transpose3d(torch.cat(xs, 1), m.weight, m.bias, stride=2, padding=1)
         if sigmoid:
             ref = torch.sigmoid(ref)
     assert y.shape == ref.shape
-    assert (y - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+    assert (y - ref).abs().max().item() <= _tol() * max(1.0, ref.abs().max().item())
 
 
 def test_dec6_two_source_path_vs_torch():
@@ -230,9 +259,8 @@ def test_dec6_two_source_path_vs_torch():
     x, s = torch.randn(1, 20, 4, 16, 16, device=DEV), torch.randn(1, 20, 4, 16, 16, device=DEV)
     with torch.no_grad():
         y = blk(x, s)
-        torch.backends.cudnn.allow_tf32 = False
-        ref = blk.net(torch.cat((x, s), 1))
-        torch.backends.cudnn.allow_tf32 = True
+        with fp32_reference():
+            ref = blk.net(torch.cat((x, s), 1))
     assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
 
 
@@ -246,11 +274,10 @@ def test_conv3d_k4s2_parity_subvolumes_vs_torch(cin, cout, b, d, h, w, monkeypat
     with torch.no_grad():
         y = ops_conv.conv3d(x, m)
         assert y is not None
-        torch.backends.cudnn.allow_tf32 = False
-        ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=1)
-        torch.backends.cudnn.allow_tf32 = True
+        with fp32_reference():
+            ref = F.conv3d(x, m.weight, m.bias, stride=2, padding=1)
     assert y.shape == ref.shape
-    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    assert (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
 
 
 def test_default_policy_routes():
@@ -287,10 +314,11 @@ def test_fused_sequential_matches_module_by_module(name):
          "VoxelDiscriminator": torch.rand(1, 1, 128, 128, 128, device=DEV)}[name]
     with torch.no_grad():
         y = net(x)
-        torch.backends.cudnn.allow_tf32 = False        # custom kernels decline: the plain modules run in fp32
-        ref = net(x)
-        torch.backends.cudnn.allow_tf32 = True
-    assert (y - ref).abs().max().item() <= 2e-2 * max(1e-3, ref.abs().max().item())
+        with fp32_reference():
+            ref = net(x)
+    tol = 2e-4 if ops_conv.PRECISION == "fp32x3" else 2e-2
+    # the critic has no normalisation layers and its scalar output is a heavily cancelling sum: floor the scale
+    assert (y - ref).abs().max().item() <= tol * max(1e-2, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("kind,cin,cout", [("convt", 1280, 320), ("convt", 200, 512)])
@@ -303,14 +331,12 @@ def test_degenerate_convolutions_as_gemm(kind, cin, cout):
         m, x = nets.Conv3d(cin, cout, 4, 1, 0).to(DEV), torch.randn(3, cin, 4, 4, 4, device=DEV, requires_grad=True)
     y = ops_conv.gemm_conv(x, m)
     assert y is not None
-    torch.backends.cudnn.allow_tf32 = False
-    ref = torch.nn.ConvTranspose3d.forward(m, x) if kind == "convt" else torch.nn.Conv3d.forward(m, x)
-    torch.backends.cudnn.allow_tf32 = True
+    with fp32_reference():
+        ref = torch.nn.ConvTranspose3d.forward(m, x) if kind == "convt" else torch.nn.Conv3d.forward(m, x)
     assert y.shape == ref.shape and (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
     g = torch.randn_like(ref)
     gx, gw = torch.autograd.grad(y, (x, m.weight), g)
-    torch.backends.cudnn.allow_tf32 = False
-    rx, rw = torch.autograd.grad(ref, (x, m.weight), g)
-    torch.backends.cudnn.allow_tf32 = True
+    with fp32_reference():
+        rx, rw = torch.autograd.grad(ref, (x, m.weight), g)
     assert (gx - rx).abs().max().item() <= 1e-4 * max(1.0, rx.abs().max().item())
     assert (gw - rw).abs().max().item() <= 1e-4 * max(1.0, rw.abs().max().item())

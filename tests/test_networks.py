@@ -72,9 +72,9 @@ def test_helpers_and_import_surface():
 @pytest.mark.parametrize("name", ["Unet_3D", "VoxelDecoder", "VoxelGenerator", "VoxelDiscriminator"])
 @pytest.mark.parametrize("tf32", [False, True])
 def test_forward_matches_reference_on_gpu(name, tf32):
-    """CUDA path against the reference digests (recorded on CPU fp32).  tf32=False: every layer in fp32 (the custom
-    TF32 kernels decline, like cuDNN honours the same switch); tf32=True: custom tcgen05 kernels where they cover the
-    layer, with the tolerance TF32's 10-bit mantissa allows through a 12-layer network."""
+    """CUDA path against the reference digests (recorded on CPU fp32).  tf32=False: the custom kernels run their
+    fp32-accurate 3xTF32 mode (cuDNN fp32 where a layer is not covered); tf32=True: single-pass fp16/TF32 operands, with
+    the tolerance a 10-bit mantissa allows through a 12-layer network."""
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     case, net, x = build(name)
@@ -88,7 +88,7 @@ def test_forward_matches_reference_on_gpu(name, tf32):
         ref = case[mode]
         assert list(y.shape) == ref["shape"]
         scale = max(1e-3, ref["abs_sum"] / y.numel())
-        tol = 2e-2 if tf32 else 2e-3
+        tol = 2e-2 if tf32 else 3e-4
         np.testing.assert_allclose(samples, ref["samples"], rtol=tol, atol=tol * scale)
         assert abs(a - ref["abs_sum"]) <= tol * max(1.0, ref["abs_sum"])
     torch.backends.cudnn.allow_tf32 = True
