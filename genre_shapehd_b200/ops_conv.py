@@ -32,7 +32,9 @@ ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
 # GENRE_B200_CONV_POLICY = comma list restricts the set ("all" = everything, the default).
 #   convt_c1_tc   the 1-channel layer on the tensor cores (3 union taps, 8 output classes as N columns); tried first
 #   gemm          ConvTranspose3d on a 1^3 input (dec1, the decoders' first layer) as one cuBLAS GEMM (0.34 -> 0.085 ms)
-_all_policy = {"convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
+#   convt_c1_train   the 1-channel layer under autograd: exact forward + custom input/weight gradients (cuDNN's wgrad: 40 ms)
+#   conv_k8s2_wgrad  Unet_3D.enc1's weight gradient (first-order backward only; double backward stays on aten)
+_all_policy = {"conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
 _default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
@@ -92,18 +94,23 @@ def _x3_operands(src0, src1):
     return _split3(t.contiguous()), None
 
 
-def _pack(module, key, make, chunk_dim):
-    """packed weights of `module` for the current mode; fp32x3: (W_hi | W_lo | W_hi) along the K-chunk axis, matching the
-    (lo | hi | hi) activation blocks: the two small cross terms are accumulated first (the tensor core's fp32 accumulator
-    truncates, so a step's error scales with the partial sum it is added to)"""
-    if not _x3():
-        return _cached_pack(module, key, make)
+def _pack(module, key, make, chunk_dim, half=None):
+    """packed weights of `module` for the current mode (cached per parameter version; repacking is one gather through the
+    layer's pack plan).  fp32x3: (W_hi | W_lo | W_hi) along the K-chunk axis, matching the (lo | hi | hi) activation
+    blocks: the two small cross terms are accumulated first (the tensor core's fp32 accumulator truncates, so a step's
+    error scales with the partial sum it is added to)."""
+    if half is None:
+        half = _f16()
+    x3 = _x3()
 
-    def make3(w):
+    def build(w):
+        plan = _pack_plan(module, key, make)
+        if not x3:
+            return _apply_plan(plan, w, half)
         hi = _tf32_hi(w)
-        p_hi, p_lo = make(hi), make(w - hi)
+        p_hi, p_lo = _apply_plan(plan, hi, False), _apply_plan(plan, w - hi, False)
         return torch.cat((p_hi, p_lo, p_hi), dim=chunk_dim).contiguous()
-    return _cached_pack(module, key + ("x3",), make3)
+    return _cached_pack(module, key + (("x3",) if x3 else ("half",) if half else ()), build)
 
 
 def _group():
@@ -211,7 +218,7 @@ def pack_convt_weights(weight, npad, group=4):
                 sub = sub.reshape(cin // (2 * g), 2, g, npad // 8, 8, t, t, t)        # (kc, kk, e, ng, r, tz, ty, tx)
                 out[pz, py, px] = sub.permute(5, 0, 6, 7, 1, 3, 4, 2)                 # (tz, kc, ty, tx, kk, ng, r, e)
     out = out.contiguous()
-    return out.half() if g == 8 else out
+    return _finish_pack(out, g)
 
 
 def pack_convt_merged_weights(weight, cpad, group=4):
@@ -240,7 +247,7 @@ def pack_convt_merged_weights(weight, cpad, group=4):
                         weq[:, c0:c0 + cout, pz, :, uy, ux] = weight[:, :, k0[pz]::2, k0[py] + 2 * ty, k0[px] + 2 * tx]
     sub = weq.reshape(cin // (2 * g), 2, g, n // 8, 8, 2, t, tu, tu)    # (kc, kk, e, ng, r, pz, tz, uy, ux)
     out = sub.permute(5, 6, 0, 7, 8, 1, 3, 4, 2).contiguous()           # (pz, tz, kc, uy, ux, kk, ng, r, e)
-    return out.half() if g == 8 else out
+    return _finish_pack(out, g)
 
 
 def pack_convt_c1_tc_weights(weight, segments, group=4):
@@ -265,12 +272,45 @@ def pack_convt_c1_tc_weights(weight, segments, group=4):
                     weq[r0:r0 + real, n, uz, uy, ux] = weight[c0:c0 + real, 0, kz, ky, kx]
     sub = weq.reshape(ktot // (2 * g), 2, g, 2, 8, 3, 3, 3)               # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()
-    return out.half() if g == 8 else out
+    return _finish_pack(out, g)
+
+
+_PLAN_MODE = False    # while True the packers run on an index tensor: no dtype conversion at the end
+
+
+def _finish_pack(out, g):
+    return out if _PLAN_MODE or g != 8 else out.half()
+
+
+def _pack_plan(module, key, make):
+    """Every packer is a pure rearrangement (copies, permutes, zero padding) of the weight entries, so it is run ONCE per
+    (layer, layout) on a tensor of 1-based element numbers; the result is a gather index + zero mask that repacks the
+    real weights with one kernel whenever they change (every optimiser step in training)."""
+    global _PLAN_MODE
+    plans = module.__dict__.setdefault("_gb_plans", {})
+    plan = plans.get(key)
+    if plan is None or plan[0].device != module.weight.device:
+        w = module.weight
+        _PLAN_MODE = True
+        try:
+            numbered = make(torch.arange(1, w.numel() + 1, dtype=torch.float64).view(w.shape))
+        finally:
+            _PLAN_MODE = False
+        idx = numbered.to(torch.int64)
+        plan = ((idx - 1).clamp_(min=0).to(w.device), (idx > 0).to(w.device))
+        plans[key] = plan
+    return plan
+
+
+def _apply_plan(plan, w, half):
+    out = torch.where(plan[1], w.reshape(-1)[plan[0]], torch.zeros((), device=w.device, dtype=w.dtype))
+    return out.half() if half else out
 
 
 def _cached_pack(module, key, make):
     """Packed weights live ON the module (they die with it; a global cache keyed by id() could hand a recycled id the
-    weights of a dead layer) and are rebuilt when the parameter is updated in place (optimizer step, load_state_dict)."""
+    weights of a dead layer) and are rebuilt when the parameter is updated in place (optimizer step, load_state_dict).
+    `key` ends with the group size g (8 = fp16 units) or ..., g, "x3"."""
     w = module.weight
     cache = module.__dict__.setdefault("_gb_packed", {})
     ver = (w._version, w.data_ptr(), str(w.device))
@@ -385,10 +425,10 @@ def pack_conv_k8s2_s4d_weights(weight, cpad, group=4, split_z=False):
     if split_z:   # [2 qz] x the 4-class (y,x) form: N = 4*cpad columns per z class
         sub = weq.reshape(cin * 64 // (2 * g), 2, g, 2, n // 16, 8, 3, 3, 3)   # (kc, kk, e, qz, ng, r, tz, ty, tx)
         out = sub.permute(3, 6, 0, 7, 8, 1, 4, 5, 2).contiguous()              # (qz, tz, kc, ty, tx, kk, ng, r, e)
-        return out.half() if g == 8 else out
+        return _finish_pack(out, g)
     sub = weq.reshape(cin * 64 // (2 * g), 2, g, n // 8, 8, 3, 3, 3)      # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                # (tz, kc, ty, tx, kk, ng, r, e)
-    return out.half() if g == 8 else out
+    return _finish_pack(out, g)
 
 
 def pack_conv_k8s2_weights(weight, npad, group=4):
@@ -416,7 +456,7 @@ def pack_conv_k8s2_weights(weight, npad, group=4):
     ceq, g = cin * 8, group
     sub = weq.reshape(ceq // (2 * g), 2, g, npad // 8, 8, t5, t5, t5)      # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                # (tz, kc, ty, tx, kk, ng, r, e)
-    return out.half() if g == 8 else out
+    return _finish_pack(out, g)
 
 
 def _packed_conv(module, npad):
@@ -464,7 +504,7 @@ def pack_conv_k4s2_weights(weight, cpad, npad, group):
                             weq[sidx, :cin, :cout, tz, ty, tx] = weight[:, :, 3 - 2 * tz - pz, 3 - 2 * ty - py, 3 - 2 * tx - px].t()
     sub = weq.reshape(8 * cpad // (2 * g), 2, g, npad // 8, 8, 2, 2, 2)           # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                        # (tz, kc, ty, tx, kk, ng, r, e)
-    return out.half() if g == 8 else out
+    return _finish_pack(out, g)
 
 
 def _conv_k4s2_supported(x, m):
@@ -528,10 +568,121 @@ def _conv_k4s2(x, m, bn, slope):
     return from_blocked(out, b, cout)
 
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class _ConvForward(torch.autograd.Function):
+    """Training: the FORWARD of a convolution on the custom kernel (conv + bias only; BatchNorm with batch statistics and
+    the activation stay torch modules), the backward on cuDNN through aten::convolution_backward.  The forward is where
+    cuDNN is furthest off its pace on these layers (Unet_3D.enc1 16.6 ms, dec5 7.3 ms at B=16)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, m):
+        transposed = isinstance(m, torch.nn.ConvTranspose3d)
+        with torch.no_grad():
+            y = (conv_transpose3d if transposed else conv3d)(x.detach(), m)
+        if y is None:
+            raise RuntimeError("ops_conv: layer not covered (the dispatcher checks support before taking this route)")
+        ctx.save_for_backward(x, weight)
+        ctx.conf = (transposed, tuple(m.stride), tuple(m.padding), tuple(m.dilation),
+                    tuple(m.output_padding) if transposed else (0, 0, 0), m.groups,
+                    [m.out_channels] if bias is not None else None)
+        y.__dict__.pop("_gb_blocked", None)        # the blocked twin must not ride along into autograd-land
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        transposed, stride, padding, dilation, out_pad, groups, bias_sizes = ctx.conf
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], bias_sizes is not None and ctx.needs_input_grad[2]]
+        gy = gy.contiguous()
+        gw_custom = None
+        if (mask[1] and not transposed and not torch.is_grad_enabled() and "conv_k8s2_wgrad" in POLICY
+                and tuple(weight.shape[2:]) == (8, 8, 8) and stride == (2, 2, 2) and padding == (3, 3, 3)
+                and dilation == (1, 1, 1) and groups == 1 and weight.shape[1] <= 2 and weight.shape[0] <= 20
+                and x.shape[3] % 16 == 0 and x.shape[4] <= 128 and x.shape[2] % 2 == 0 and x.shape[4] % 2 == 0):
+            # Unet_3D.enc1: cuDNN's wgrad for this shape is a 40 ms grouped direct kernel (csrc/convt_c1_wgrad.cu)
+            xc = x.contiguous()
+            nbytes = _lib.load().genre_b200_conv_k8s2_wgrad_workspace_bytes()
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            gw_custom = torch.empty_like(weight)
+            _lib.call("genre_b200_conv_k8s2_wgrad", xc.data_ptr(), gy.data_ptr(), x.shape[0], weight.shape[1], weight.shape[0],
+                      x.shape[2], x.shape[3], x.shape[4], gw_custom.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr(x))
+            mask[1] = False
+        gx = gw = gb = None
+        if any(mask):
+            gx, gw, gb = torch.ops.aten.convolution_backward(gy, x, weight, bias_sizes, list(stride), list(padding),
+                                                              list(dilation), transposed, list(out_pad), groups, mask)
+        return gx, (gw_custom if gw_custom is not None else gw), gb, None
+
+
+class _ConvTC1Train(torch.autograd.Function):
+    """ConvTranspose3d(Cin -> 1, k4, s2, p1) under autograd (Unet_3D.dec6 and the decoders' last layers in training).
+    cuDNN's weight gradient for this 1-channel layer is a grouped direct kernel that takes 40.7 of the 60 ms of a Unet_3D
+    training step at B=4; here forward = the exact-fp32 FP32-pipe stencil (csrc/convt_c1.cu), input and weight gradients
+    = csrc/convt_c1_wgrad.cu (deterministic), bias gradient = a sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, m):
+        with torch.no_grad():
+            xd = x.detach().contiguous()
+            y = convt_c1(to_blocked(xd, 4), None, xd.shape[0], m)
+        ctx.save_for_backward(xd, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        b, cin, d, h, w = x.shape
+        st = _lib.stream_ptr(x)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _lib.call("genre_b200_convt_c1_dgrad", gy.data_ptr(), weight.detach().contiguous().data_ptr(), b, cin, d, h, w,
+                      gx.data_ptr(), st)
+        if ctx.needs_input_grad[1]:
+            nbytes = _lib.load().genre_b200_convt_c1_wgrad_workspace_bytes(cin)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            gw = torch.empty_like(weight)
+            _lib.call("genre_b200_convt_c1_wgrad", x.data_ptr(), gy.data_ptr(), b, cin, d, h, w, gw.data_ptr(),
+                      ws.data_ptr(), nbytes, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum().reshape(1)
+        return gx, gw, gb, None
+
+
+def _convt_c1_train_supported(x, m):
+    return (ENABLED and "convt_c1_train" in POLICY and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+            and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1)
+            and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1
+            and m.out_channels == 1 and x.shape[1] % 4 == 0 and x.shape[1] <= 48 and x.shape[3] % 8 == 0
+            and x.shape[4] % 4 == 0 and x.shape[4] <= 64)
+
+
+TRAIN_FORWARD = os.environ.get("GENRE_B200_CONV_TRAIN_FORWARD", "1") != "0"
+
+
+def _train_forward(x, m, supported):
+    """conv-only call under autograd: custom forward + cuDNN backward when the layer is covered, else None"""
+    if not (TRAIN_FORWARD and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and supported):
+        return None
+    return _ConvForward.apply(x, m.weight, m.bias, m)
+
+
 def conv3d(x, m, bn=None, slope=None):
     """Conv3d on the tcgen05 kernel [+ folded eval BatchNorm3d + LeakyReLU]: k=8,s=2,p=3 on few input channels
     (Unet_3D.enc1) via space-to-depth, or k=4,s=2,p=1 (discriminator, Unet_3D.enc2/enc3) via parity sub-volumes."""
-    if not x.is_cuda or not _no_autograd(x, m.weight, m.bias):
+    if not x.is_cuda:
+        return None
+    if _needs_grad(x, m.weight, m.bias):
+        if bn is not None or slope is not None:
+            return None     # fused epilogues are inference-only; the caller falls back to module-by-module
+        return _train_forward(x, m, _conv_k4s2_supported(x, m) or _conv_k8s2_supported(x, m))
+    if not _no_autograd(x, m.weight, m.bias):
         return None
     if _conv_k4s2_supported(x, m):
         return _conv_k4s2(x, m, bn, slope)
@@ -610,7 +761,7 @@ def convt_c1_tc(inputs, m, sigmoid=False):
     segments = tuple((t.shape[1], o[1]) for t, o in zip(inputs, ops))
     if sum(pc for _, pc in segments) % (2 * g) != 0:
         return None
-    wpack = _cached_pack(m, ("c1_tc", segments, g), lambda wt: pack_convt_c1_tc_weights(wt, segments, g))
+    wpack = _pack(m, ("c1_tc", segments, g), lambda wt: pack_convt_c1_tc_weights(wt, segments, g), 1)
     b, _, d, h, w = x0.shape
     if m.bias is not None:
         bias = m.bias.detach()
@@ -662,6 +813,12 @@ def convt_c1(src0, src1, batch, m):
 def conv_transpose3d(x, m, bn=None, slope=None):
     """ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> ReLU / LeakyReLU(slope)]; None if not covered
     (the caller then runs the plain modules)."""
+    if x.is_cuda and not isinstance(x, BlockedActivation) and _needs_grad(x, m.weight, m.bias):
+        if bn is not None or slope is not None:
+            return None
+        if TRAIN_FORWARD and _convt_c1_train_supported(x, m):
+            return _ConvTC1Train.apply(x, m.weight, m.bias, m)
+        return _train_forward(x, m, m.out_channels > 1 and _convt_supported(x.shape, m))
     if bn is None and slope is None and m.out_channels == 1:
         y = convt_c1_tc((x,), m)
         if y is not None:

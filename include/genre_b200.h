@@ -244,6 +244,26 @@ int genre_b200_convt_c1_tc_forward(const void *src0, int cg0, const void *src1, 
                                    const void *wpack, int f16, const float *bias, int act_sigmoid,
                                    float *out, void *stream);
 
+/* Backward of ConvTranspose3d(Cin -> 1, k 4, s 2, p 1) (Unet_3D.dec6 networks/networks.py:167-168 and the decoders' last
+ * layers): cuDNN answers the weight gradient of this 1-channel layer with a grouped direct kernel that takes 40.7 ms of
+ * a 60 ms Unet_3D training step at B=4 (profiles/r01_train_unet_launches.csv).
+ *   wgrad: x [B][Cin][D][H][W], gy [B][1][2D][2H][2W] -> dW [Cin][1][4][4][4]; deterministic (fixed-order reduction of
+ *          per-CTA partials in `workspace`, genre_b200_convt_c1_wgrad_workspace_bytes(Cin) bytes); Cin <= 64, H % 8 == 0.
+ *   dgrad: gy, weight -> dx [B][Cin][D][H][W]; Cin <= 192, H % 8 == 0. */
+size_t genre_b200_convt_c1_wgrad_workspace_bytes(int cin);
+int genre_b200_convt_c1_wgrad(const float *x, const float *gy, int64_t B, int64_t Cin, int64_t D, int64_t H, int64_t W,
+                              float *dW, void *workspace, size_t workspace_bytes, void *stream);
+int genre_b200_convt_c1_dgrad(const float *gy, const float *weight, int64_t B, int64_t Cin, int64_t D, int64_t H, int64_t W,
+                              float *dx, void *stream);
+
+/* Weight gradient of Conv3d(Cin <= 2 -> Cout <= 20, k 8, s 2, p 3) = Unet_3D.enc1 (networks/networks.py:151): the
+ * cuDNN kernel for it (wgrad2d_grouped_direct_kernel) is 40.7 ms of a 60 ms Unet_3D training step at B=4.
+ * x [B][Cin][D][H][W], gy [B][Cout][D/2][H/2][W/2] -> dW [Cout][Cin][8][8][8]; deterministic; H % 16 == 0, W <= 128. */
+size_t genre_b200_conv_k8s2_wgrad_workspace_bytes(void);
+int genre_b200_conv_k8s2_wgrad(const float *x, const float *gy, int64_t B, int64_t Cin, int64_t Cout,
+                               int64_t D, int64_t H, int64_t W, float *dW,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* Layout boundary of the convolution kernels: contiguous NCDHW fp32 (what networks/networks.py's modules exchange,
  * e.g. Unet_3D.forward networks.py:170-190) <-> channel-blocked [B*D][C/g][H][W][g] (16 bytes per unit).
  *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1);

@@ -161,3 +161,22 @@ def test_space_to_depth_channel_order(group):
     for ch in range(16):
         c, pz, py, px = ch // 8, (ch // 4) % 2, (ch // 2) % 2, ch % 2
         assert torch.equal(y[2:, ch // g, :, :, ch % g], x[1, c, pz::2, py::2, px::2])
+
+
+def test_pack_plans_reproduce_the_packers():
+    """ops_conv._pack repacks through a gather index derived from the packer once per layer: same bytes as the packer"""
+    import torch.nn as nn
+    torch.manual_seed(12)
+    m = nn.ConvTranspose3d(16, 5, 8, 2, 3)
+    for g in (4, 8):
+        direct = ops_conv.pack_convt_merged_weights(m.weight.detach(), 8, g)
+        via_plan = ops_conv._pack(m, ("convt_merged", 8, g), lambda wt: ops_conv.pack_convt_merged_weights(wt, 8, g), 2, half=(g == 8))
+        assert via_plan.dtype == direct.dtype and torch.equal(via_plan, direct)
+    c = nn.Conv3d(5, 6, 4, 2, 1)
+    direct = ops_conv.pack_conv_k4s2_weights(c.weight.detach(), 8, 8, 4)
+    via_plan = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
+    assert torch.equal(via_plan, direct)
+    with torch.no_grad():
+        c.weight.mul_(2.0)                                   # in-place update (optimizer step): the cache must follow
+    again = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
+    assert torch.equal(again, direct * 2)

@@ -134,10 +134,12 @@ def test_deconv_skip_fused_bn_leaky_vs_torch():
     assert (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
 
 
-def test_autograd_and_unsupported_shapes_fall_back():
+def test_autograd_and_unsupported_shapes_fall_back(monkeypatch):
     m = nets.ConvTranspose3d(16, 4, 4, 2, 1).to(DEV)
     x = torch.randn(1, 16, 2, 16, 16, device=DEV, requires_grad=True)
-    assert ops_conv.conv_transpose3d(x, m) is None             # autograd: cuDNN path
+    assert ops_conv.conv_transpose3d(x, m, None, 0.0) is None  # fused epilogues are inference-only
+    monkeypatch.setattr(ops_conv, "TRAIN_FORWARD", False)
+    assert ops_conv.conv_transpose3d(x, m) is None             # autograd with the training forward off: cuDNN path
     y = m(x)
     y.sum().backward()
     assert x.grad is not None
@@ -340,3 +342,79 @@ def test_degenerate_convolutions_as_gemm(kind, cin, cout):
         rx, rw = torch.autograd.grad(ref, (x, m.weight), g)
     assert (gx - rx).abs().max().item() <= 1e-4 * max(1.0, rx.abs().max().item())
     assert (gw - rw).abs().max().item() <= 1e-4 * max(1.0, rw.abs().max().item())
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,shape", [("conv", 2, 20, 8, (2, 8, 64, 64)), ("conv", 24, 40, 4, (2, 8, 64, 64)),
+                                                   ("convt", 80, 20, 8, (1, 2, 32, 32)), ("convt", 64, 32, 4, (2, 2, 16, 16))])
+def test_training_forward_on_custom_kernel_backward_on_cudnn(kind, cin, cout, k, shape):
+    """under autograd the conv-only forward runs on the custom kernel and the backward is aten::convolution_backward:
+    outputs and all three gradients against the plain cuDNN module"""
+    torch.manual_seed(cin + cout)
+    b, d, h, w = shape
+    m = (nets.Conv3d(cin, cout, k, 2, k // 2 - 1) if kind == "conv" else nets.ConvTranspose3d(cin, cout, k, 2, k // 2 - 1)).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV, requires_grad=True)
+    y = m(x)
+    assert y.grad_fn is not None and "ConvForward" in type(y.grad_fn).__name__
+    g = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, (x, m.weight, m.bias), g)
+    with fp32_reference():
+        ref = m(x)
+        rx, rw, rb = torch.autograd.grad(ref, (x, m.weight, m.bias), g)
+    assert (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
+    for a, r in ((gx, rx), (gw, rw), (gb, rb)):     # backward itself ran on cuDNN with TF32 allowed
+        assert (a - r).abs().max().item() <= 4e-3 * r.abs().max().item()
+
+
+def test_training_forward_supports_double_backward():
+    """WGAN-GP differentiates the critic's input gradient (wgangp.py:144-164): the wrapper's backward is built from
+    differentiable aten ops"""
+    torch.manual_seed(9)
+    m = nets.Conv3d(64, 64, 4, 2, 1, bias=False).to(DEV)
+    x = torch.randn(1, 64, 4, 32, 32, device=DEV, requires_grad=True)
+    y = m(x)
+    (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+    pen = (gx.norm() - 1) ** 2
+    pen.backward()
+    assert m.weight.grad is not None and torch.isfinite(m.weight.grad).all() and m.weight.grad.abs().sum().item() > 0
+
+
+@pytest.mark.parametrize("cin,b,d,h,w", [(40, 2, 3, 16, 64), (32, 1, 4, 8, 16), (8, 3, 2, 24, 20)])
+def test_convt_one_channel_training_path_vs_cudnn(cin, b, d, h, w):
+    """ConvT(Cin -> 1) under autograd: exact-fp32 forward, custom dgrad and (deterministic) wgrad against cuDNN fp32"""
+    torch.manual_seed(cin + w)
+    m = nets.ConvTranspose3d(cin, 1, 4, 2, 1).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV, requires_grad=True)
+    y = m(x)
+    assert "ConvTC1Train" in type(y.grad_fn).__name__
+    g = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, (x, m.weight, m.bias), g, retain_graph=True)
+    gw2 = torch.autograd.grad(y, m.weight, g)[0]
+    assert torch.equal(gw, gw2)                              # fixed-order reduction: bitwise reproducible
+    with fp32_reference():
+        ref = m(x)
+        rx, rw, rb = torch.autograd.grad(ref, (x, m.weight, m.bias), g)
+    for a, r in ((y, ref), (gx, rx), (gw, rw), (gb, rb)):
+        assert a.shape == r.shape and (a - r).abs().max().item() <= 2e-5 * max(1.0, r.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,b,d,h,w", [(2, 20, 2, 4, 32, 64), (1, 7, 1, 6, 16, 20), (2, 20, 1, 2, 64, 128)])
+def test_conv_k8s2_weight_gradient_vs_cudnn(cin, cout, b, d, h, w):
+    """csrc/convt_c1_wgrad.cu conv_k8s2_wgrad (Unet_3D.enc1's dW) against cuDNN fp32; bitwise reproducible"""
+    torch.manual_seed(cout + w)
+    x = torch.randn(b, cin, d, h, w, device=DEV)
+    wt = torch.randn(cout, cin, 8, 8, 8, device=DEV, requires_grad=True)
+    with fp32_reference():
+        y = F.conv3d(x, wt, None, stride=2, padding=3)
+        g = torch.randn_like(y)
+        (ref,) = torch.autograd.grad(y, wt, g)
+    from genre_shapehd_b200 import _lib
+    nbytes = _lib.load().genre_b200_conv_k8s2_wgrad_workspace_bytes()
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    outs = []
+    for _ in range(2):
+        dw = torch.empty_like(wt)
+        _lib.call("genre_b200_conv_k8s2_wgrad", x.data_ptr(), g.data_ptr(), b, cin, cout, d, h, w, dw.data_ptr(), ws.data_ptr(),
+                  nbytes, _lib.stream_ptr(x))
+        outs.append(dw)
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0] - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
