@@ -658,7 +658,7 @@ extern "C" int genre_b200_convt_c1_tc_forward(const void *src0_, int cg0, const 
 // A strided Conv3d reaches this form through space-to-depth (genre_shapehd_b200/ops_conv.py): Unet_3D.enc1 =
 // Conv3d(2 -> 20, k=8, s=2, p=3) (networks/networks.py:151) is a 5-tap stride-1 convolution over the 16 s2d channels.
 //   wpack [T z-tap][C/8 chunk][T*T taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4]
-// Supported: T in {3, 5}, W in {16, 32, 64}, H % 16 == 0, npad = 32.
+// Supported: T in {3, 5}, W in {16, 32, 64}, H % 16 == 0, npad = 32 (or 64 with T = 3).
 extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
                                               int64_t D, int64_t H, int64_t W, const void *wpack_, int taps, int base,
                                               int npad, int f16, const float *scale, const float *shift, float slope,
@@ -667,7 +667,7 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   g_conv_f16 = f16 != 0;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_taps: null pointer");
   GB_REQUIRE(taps == 3 || taps == 5, GENRE_B200_EINVAL, "conv3d_taps: %d taps unsupported (3 or 5)", taps);
-  GB_REQUIRE(npad == 32, GENRE_B200_EINVAL, "conv3d_taps: npad %d unsupported (32)", npad);
+  GB_REQUIRE(npad == 32 || (npad == 64 && taps == 3), GENRE_B200_EINVAL, "conv3d_taps: npad %d unsupported (32; 64 with 3 taps)", npad);
   GB_REQUIRE(W == 16 || W == 32 || W == 64, GENRE_B200_EINVAL, "conv3d_taps: width %lld unsupported", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_taps: bad extent");
   GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
@@ -683,6 +683,12 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   p.srcpar_cgs = 0;
   p.base[0] = p.base[1] = base;
   cudaStream_t st = as_stream(stream);
+  // 3 taps, N = 64: Conv3d(1 -> 64, k4, s2, p1) over the 2x space-to-depth input (VoxelDiscriminator's first layer);
+  // 32-wide tiles (256 TMEM columns) so that two CTAs share an SM
+  if (taps == 3 && npad == 64) {
+    if (W % 32 == 0) return launch_convt<3, 64, 4, false>(p, st);
+    return launch_convt<3, 64, 2, false>(p, st);
+  }
 #define GB_CV(TT, MM) return launch_convt<TT, 32, MM, false>(p, st)
   if (taps == 5 && W == 64) GB_CV(5, 8);
   if (taps == 5 && W == 32) GB_CV(5, 4);

@@ -56,9 +56,9 @@ to_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, 
 // one thread = one output position (z', y', x') of one input channel c: reads the 2x2x2 cell as four float2
 template <int G>
 __global__ void __launch_bounds__(LY_THREADS)
-s2d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t cells) {
+s2d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t cells,
+                   int CGo /* channel groups of dst (>= C*8/G; the extra ones were zero-filled by the launcher) */) {
   const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
-  const int CGo = C * 8 / G;
   for (size_t i = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; i < cells; i += (size_t)gridDim.x * LY_THREADS) {
     const int x2 = (int)(i % W2);
     size_t r = i / W2;
@@ -263,8 +263,15 @@ extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t 
   GB_REQUIRE(((uintptr_t)src & 7) == 0, GENRE_B200_EALIGN, "space-to-depth: src must be 8-byte aligned");
   if (mode == 1) {
     const size_t cells = (size_t)(B * C * (D / 2) * (H / 2) * (W / 2));
-    if (group == 4) s2d_blocked_kernel<4><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells);
-    else s2d_blocked_kernel<8><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells);
+    int cgo = (int)(C * 8 / group);
+    if (cpad > C * 8) {  // pad the 8C space-to-depth channels with zero groups up to cpad channels
+      GB_REQUIRE(cpad % group == 0, GENRE_B200_EINVAL, "s2d_blocked: cpad=%d not a multiple of %d", cpad, group);
+      cgo = cpad / group;
+      cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)(B * (D / 2)) * cgo * (size_t)((H / 2) * (W / 2)) * 16, st);
+      if (e != cudaSuccess) return fail_arg((int)e, "s2d_blocked: memset: %s", cudaGetErrorString(e));
+    }
+    if (group == 4) s2d_blocked_kernel<4><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells, cgo);
+    else s2d_blocked_kernel<8><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells, cgo);
     return check_launch("s2d_blocked kernel");
   }
   if (mode == 3) {

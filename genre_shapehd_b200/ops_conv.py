@@ -34,7 +34,9 @@ ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
 #   gemm          ConvTranspose3d on a 1^3 input (dec1, the decoders' first layer) as one cuBLAS GEMM (0.34 -> 0.085 ms)
 #   convt_c1_train   the 1-channel layer under autograd: exact forward + custom input/weight gradients (cuDNN's wgrad: 40 ms)
 #   conv_k8s2_wgrad  Unet_3D.enc1's weight gradient (first-order backward only; double backward stays on aten)
-_all_policy = {"conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
+#   conv_k4s2_s2d    Conv3d(1 or 2 -> 64, k4 s2) as 3 taps over the 2x space-to-depth input (VoxelDiscriminator main.0:
+#                    cuDNN 2.6 ms in eval at B=16 and a 35 ms kernel per call in the WGAN-GP step at B=8)
+_all_policy = {"conv_k4s2_s2d", "conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
 _default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
@@ -370,15 +372,21 @@ def _no_autograd(*tensors):
     return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
 
-def space_to_depth_blocked(x, group=4, dtype=None):
+def space_to_depth_blocked(x, group=4, dtype=None, cpad=0):
     """NCDHW [B,C,D,H,W] (even extents, group | 8) -> blocked [B*D/2, C*8/group, H/2, W/2, group] whose channel
-    index is ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px)."""
+    index is ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px); cpad > 8C appends zero channels."""
     b, c, d, h, w = x.shape
     assert 8 % group == 0
     if _on_device(x, group, dtype):
-        out = torch.empty((b * (d // 2), c * 8 // group, h // 2, w // 2, group), device=x.device, dtype=dtype or x.dtype)
-        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 1, group, 0, out.data_ptr(), _lib.stream_ptr(x))
+        ncg = max(c * 8, cpad) // group
+        out = torch.empty((b * (d // 2), ncg, h // 2, w // 2, group), device=x.device, dtype=dtype or x.dtype)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 1, group, cpad if cpad > c * 8 else 0,
+                  out.data_ptr(), _lib.stream_ptr(x))
         return out
+    if cpad > c * 8:
+        y = space_to_depth_blocked(x, group, dtype)
+        pad = y.new_zeros((y.shape[0], (cpad - c * 8) // group) + tuple(y.shape[2:]))
+        return torch.cat((y, pad), dim=1)
     s = 8 // group                                       # channel groups per input channel
     # pz,py,px bits split as (j, e) with j the top log2(s) bits: view dims b c z' pz y' py x' px
     t = x.reshape(b, c, d // 2, 2, h // 2, 2, w // 2, 2)
@@ -429,6 +437,57 @@ def pack_conv_k8s2_s4d_weights(weight, cpad, group=4, split_z=False):
     sub = weq.reshape(cin * 64 // (2 * g), 2, g, n // 8, 8, 3, 3, 3)      # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                # (tz, kc, ty, tx, kk, ng, r, e)
     return _finish_pack(out, g)
+
+
+def pack_conv_k4s2_s2d_weights(weight, cpad, npad, group=4):
+    """Conv3d weight [Cout, Cin, 4, 4, 4] (stride 2, padding 1), FEW input channels -> the 3-tap stride-1 convolution over the
+    8*Cin space-to-depth channels (zero-padded to cpad): [3 z-tap][cpad/(2g)][9 taps][2][npad/8][8][g].  Per dimension:
+    output o reads input 2o - 1 + k = 2(o + 1 - t) + r  =>  k = 3 - 2t + r (zero weight outside [0, 4))."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    g = group
+    t = torch.arange(3).view(3, 1)
+    r = torch.arange(2).view(1, 2)
+    k = 3 - 2 * t + r                                                       # [t, r]
+    valid = ((k >= 0) & (k < 4)).to(weight.device)
+    kc = k.clamp(0, 3).to(weight.device)
+    kz, vz = kc.view(3, 2, 1, 1, 1, 1), valid.view(3, 2, 1, 1, 1, 1)
+    ky, vy = kc.view(1, 1, 3, 2, 1, 1), valid.view(1, 1, 3, 2, 1, 1)
+    kx, vx = kc.view(1, 1, 1, 1, 3, 2), valid.view(1, 1, 1, 1, 3, 2)
+    full = weight[:, :, kz, ky, kx] * (vz & vy & vx).to(weight.dtype)        # [co, c, tz,rz, ty,ry, tx,rx]
+    weq = full.permute(1, 3, 5, 7, 0, 2, 4, 6).reshape(cin * 8, cout, 3, 3, 3)   # (c rz ry rx | co | tz ty tx)
+    weq = torch.nn.functional.pad(weq, (0, 0, 0, 0, 0, 0, 0, npad - cout, 0, cpad - cin * 8))
+    sub = weq.reshape(cpad // (2 * g), 2, g, npad // 8, 8, 3, 3, 3)          # (kc, kk, e, ng, r, tz, ty, tx)
+    out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()                   # (tz, kc, ty, tx, kk, ng, r, e)
+    return _finish_pack(out, g)
+
+
+def _conv_k4s2_s2d_supported(x, m):
+    """few input channels (the critic's 1 -> 64 first layer): the 8*Cin space-to-depth channels fit one K chunk"""
+    return ("conv_k4s2_s2d" in POLICY and ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+            and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2) and tuple(m.padding) == (1, 1, 1)
+            and tuple(m.dilation) == (1, 1, 1) and m.groups == 1 and m.padding_mode == "zeros" and x.shape[1] <= 2
+            and 32 < m.out_channels <= 64 and all(v % 2 == 0 for v in x.shape[2:]) and x.shape[4] // 2 in (16, 32, 64)
+            and (x.shape[3] // 2) % 16 == 0)
+
+
+def _conv_k4s2_s2d(x, m, bn, slope):
+    cout, npad, g = m.out_channels, 64, _group()
+    aff = _affine(m, bn, npad, x.device)
+    if aff is None:
+        return None
+    cpad = -(-x.shape[1] * 8 // (2 * g)) * 2 * g          # the 8*Cin channels rounded up to whole K chunks
+    wpack = _pack(m, ("k4s2_s2d", cpad, npad, g), lambda w: pack_conv_k4s2_s2d_weights(w, cpad, npad, g), 1)
+    xb = space_to_depth_blocked(x, g, torch.float16 if _f16() else None, cpad)
+    if _x3():
+        xb = _split3(xb)
+    b = x.shape[0]
+    bd, cg, h, w, _ = xb.shape
+    cgo = (cout + 3) // 4
+    out = torch.empty((bd, cgo, h, w, 4), device=x.device, dtype=torch.float32)
+    _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg, None, 0, b, bd // b, h, w, wpack.data_ptr(), 3, 1, npad,
+              1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
+              out.data_ptr(), cgo, _lib.stream_ptr(x))
+    return from_blocked(out, b, cout)
 
 
 def pack_conv_k8s2_weights(weight, npad, group=4):
@@ -572,6 +631,39 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+class _ConvInputGrad(torch.autograd.Function):
+    """Input gradient of a Conv3d as a differentiable node of its own, used when the first backward is recorded
+    (create_graph=True: WGAN-GP's gradient penalty, wgangp.py:144-164).  Its derivative with respect to the incoming
+    gradient is the layer's FORWARD convolution applied to the grad-of-grad, which autograd would otherwise hand to cuDNN
+    (for the critic's layers: three 35 ms kernels, 106 of the 142 ms of a critic step at B=8); here it runs on the custom
+    forward kernel."""
+
+    @staticmethod
+    def forward(ctx, gy, weight, x, m):
+        conf = (list(m.stride), list(m.padding), list(m.dilation), False, [0, 0, 0], m.groups)
+        gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, *conf, [True, False, False])
+        ctx.save_for_backward(gy, weight)
+        ctx.m, ctx.conf = m, conf
+        return gx
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ggx):
+        gy, weight = ctx.saved_tensors
+        m = ctx.m
+        ggx = ggx.contiguous()
+        g_gy = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_gy = conv3d(ggx, m)                      # no grad mode here: the custom forward kernel (bias is not part of it)
+            if g_gy is None:
+                g_gy = torch.nn.functional.conv3d(ggx, weight, None, m.stride, m.padding, m.dilation, m.groups)
+            elif m.bias is not None:
+                g_gy = g_gy - m.bias.detach().view(1, -1, 1, 1, 1)
+        if ctx.needs_input_grad[1]:
+            _, g_w, _ = torch.ops.aten.convolution_backward(gy, ggx, weight, None, *ctx.conf, [False, True, False])
+        return g_gy, g_w, None, None
+
+
 class _ConvForward(torch.autograd.Function):
     """Training: the FORWARD of a convolution on the custom kernel (conv + bias only; BatchNorm with batch statistics and
     the activation stay torch modules), the backward on cuDNN through aten::convolution_backward.  The forward is where
@@ -585,6 +677,7 @@ class _ConvForward(torch.autograd.Function):
         if y is None:
             raise RuntimeError("ops_conv: layer not covered (the dispatcher checks support before taking this route)")
         ctx.save_for_backward(x, weight)
+        ctx.module = m
         ctx.conf = (transposed, tuple(m.stride), tuple(m.padding), tuple(m.dilation),
                     tuple(m.output_padding) if transposed else (0, 0, 0), m.groups,
                     [m.out_channels] if bias is not None else None)
@@ -611,10 +704,14 @@ class _ConvForward(torch.autograd.Function):
                       x.shape[2], x.shape[3], x.shape[4], gw_custom.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr(x))
             mask[1] = False
         gx = gw = gb = None
+        gx_custom = None
+        if mask[0] and torch.is_grad_enabled() and not transposed and ctx.module is not None:
+            gx_custom = _ConvInputGrad.apply(gy, weight, x, ctx.module)   # double backward stays on the custom forward
+            mask[0] = False
         if any(mask):
             gx, gw, gb = torch.ops.aten.convolution_backward(gy, x, weight, bias_sizes, list(stride), list(padding),
                                                               list(dilation), transposed, list(out_pad), groups, mask)
-        return gx, (gw_custom if gw_custom is not None else gw), gb, None
+        return (gx_custom if gx_custom is not None else gx), (gw_custom if gw_custom is not None else gw), gb, None
 
 
 class _ConvTC1Train(torch.autograd.Function):
@@ -681,11 +778,13 @@ def conv3d(x, m, bn=None, slope=None):
     if _needs_grad(x, m.weight, m.bias):
         if bn is not None or slope is not None:
             return None     # fused epilogues are inference-only; the caller falls back to module-by-module
-        return _train_forward(x, m, _conv_k4s2_supported(x, m) or _conv_k8s2_supported(x, m))
+        return _train_forward(x, m, _conv_k4s2_supported(x, m) or _conv_k8s2_supported(x, m) or _conv_k4s2_s2d_supported(x, m))
     if not _no_autograd(x, m.weight, m.bias):
         return None
     if _conv_k4s2_supported(x, m):
         return _conv_k4s2(x, m, bn, slope)
+    if _conv_k4s2_s2d_supported(x, m):
+        return _conv_k4s2_s2d(x, m, bn, slope)
     if not _conv_k8s2_supported(x, m):
         return None
     if MERGE_PARITIES and m.out_channels <= 20 and all(v % 64 == 0 for v in x.shape[3:]) and x.shape[2] % 4 == 0:

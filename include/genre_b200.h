@@ -191,7 +191,8 @@ int genre_b200_convt3d_s2_forward(const void *src0, int cg0, const void *src1, i
  *   out[b,z,y,x,n] = act(scale[n] * sum_{t,c} in[b, z+base-tz, y+base-ty, x+base-tx, c] * W[t][c][n] + shift[n])
  * Replaces the cuDNN call behind nn.Conv3d of Unet_3D.enc1 (networks/networks.py:151,197: Conv3d(2->20, k=8, s=2, p=3))
  * after a space-to-depth of the input (k=8/s=2 over C channels == 5 taps/s=1 over 8C channels).
- *   wpack [taps][C/8][taps*taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4];  W in {16,32,64}, H % 16 == 0, npad = 32 */
+ *   wpack [taps][C/8][taps*taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4];  W in {16,32,64}, H % 16 == 0, npad = 32
+ *   (npad = 64 with 3 taps: Conv3d(1 -> 64, k4, s2, p1) over the 2x space-to-depth input, VoxelDiscriminator main.0) */
 int genre_b200_conv3d_taps_forward(const void *src0, int cg0, const void *src1, int cg1,
                                    int64_t B, int64_t D, int64_t H, int64_t W,
                                    const void *wpack, int taps, int base, int npad, int f16,
@@ -266,7 +267,8 @@ int genre_b200_conv_k8s2_wgrad(const float *x, const float *gy, int64_t B, int64
 
 /* Layout boundary of the convolution kernels: contiguous NCDHW fp32 (what networks/networks.py's modules exchange,
  * e.g. Unet_3D.forward networks.py:170-190) <-> channel-blocked [B*D][C/g][H][W][g] (16 bytes per unit).
- *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1);
+ *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1; with cpad > 8C the
+ *           channel axis is zero-padded to cpad channels: Conv3d(1 -> 64, k4 s2), VoxelDiscriminator's first layer);
  *   mode 2: the 8 parity sub-volumes one after the other, each padded to cpad channels (Conv3d k4 s2);
  *   mode 3: 4x space-to-depth, channel = ((c*4+rz)*4+ry)*4+rx (Conv3d k8 s2 as a 3-tap convolution, Unet_3D.enc1).
  *   group 4: fp32 units, group 8: fp16 units (cast on the way).  One pass, 16-byte stores. */

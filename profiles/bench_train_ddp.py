@@ -5,7 +5,9 @@ decoder is fed random 200-d codes directly; everything 3D is the reference's gra
   shapehd step : models/shapehd.py:67-79,113-118  VoxelDecoder -> sigmoid -> frozen D; loss = BCE + w * -mean(D(.))
   wgangp D step: models/wgangp.py:77-142,144-164  D(real), D(G(z)) and the gradient penalty (double backward through D),
                  accumulated with no_sync() so the three backward() calls cost one all-reduce
-Training uses autograd, so the convolutions run on cuDNN here (the tcgen05 kernels are forward-only in this round).
+Under autograd the covered layers run their forward on the custom kernels and their backward on cuDNN / the custom
+weight-gradient kernels (ops_conv._ConvForward, _ConvTC1Train); GENRE_B200_CONV_TRAIN_FORWARD=0 gives the all-cuDNN step.
+NCU=shapehd|wgan: run one warm step of that kind between cudaProfilerStart/Stop (for `ncu --profile-from-start off`).
 
     torchrun --nproc-per-node N profiles/bench_train_ddp.py [--steps K]          # one JSON line from rank 0
 """
@@ -88,7 +90,13 @@ def bench(fn):
     ms = dist_util.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     return ms, float(last)
 
-res = {"n_gpus": world, "batch_per_gpu": B, "steps": args.steps}
+if os.environ.get("NCU"):
+    fn = shapehd_step if os.environ["NCU"] == "shapehd" else wgan_d_step
+    for _ in range(2): fn()
+    torch.cuda.synchronize(); torch.cuda.profiler.start(); fn(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
+    sys.exit(0)
+from genre_shapehd_b200 import ops_conv
+res = {"n_gpus": world, "batch_per_gpu": B, "steps": args.steps, "train_forward_custom": ops_conv.TRAIN_FORWARD}
 ms, loss = bench(shapehd_step)
 res["shapehd_step_ms"] = ms
 res["shapehd_shapes_per_s"] = world * B / ms * 1e3

@@ -180,3 +180,19 @@ def test_pack_plans_reproduce_the_packers():
         c.weight.mul_(2.0)                                   # in-place update (optimizer step): the cache must follow
     again = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
     assert torch.equal(again, direct * 2)
+
+
+def test_pack_conv_k4s2_s2d_weights_few_input_channels():
+    """VoxelDiscriminator's first layer Conv3d(1 -> 64, k4 s2 p1): 3 taps over the zero-padded 2x space-to-depth channels"""
+    torch.manual_seed(14)
+    for cin in (1, 2):
+        cout, cpad, npad, g = 6, 16, 8, 4
+        wt = torch.randn(cout, cin, 4, 4, 4)
+        x = torch.randn(2, cin, 4, 6, 8)
+        ref = F.conv3d(x.double(), wt.double(), stride=2, padding=1)
+        wp = ops_conv.pack_conv_k4s2_s2d_weights(wt, cpad, npad, g)
+        assert wp.shape == (3, cpad // (2 * g), 3, 3, 2, 1, 8, g)
+        xb = ops_conv.space_to_depth_blocked(x, g, None, cpad)
+        assert xb.shape[1] == cpad // g
+        y = _taps_gemm(xb, 2, wp, 1, 1, 1)[..., :cout].permute(0, 4, 1, 2, 3)
+        assert torch.allclose(y, ref, atol=1e-5)

@@ -418,3 +418,46 @@ def test_conv_k8s2_weight_gradient_vs_cudnn(cin, cout, b, d, h, w):
         outs.append(dw)
     assert torch.equal(outs[0], outs[1])
     assert (outs[0] - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,b,d,h,w", [(1, 64, 2, 4, 64, 128), (2, 40, 1, 6, 32, 32), (1, 64, 1, 2, 32, 64)])
+def test_conv3d_k4s2_few_input_channels_vs_torch(cin, cout, b, d, h, w):
+    """VoxelDiscriminator main.0 (Conv3d 1 -> 64, k4 s2 p1 + LeakyReLU) as 3 taps over the space-to-depth input"""
+    torch.manual_seed(cin + cout + w)
+    m = nets.Conv3d(cin, cout, 4, 2, 1, bias=False).to(DEV)
+    x = torch.rand(b, cin, d, h, w, device=DEV)
+    with torch.no_grad():
+        y = ops_conv.conv3d(x, m, None, 0.2)
+        assert y is not None
+        with fp32_reference():
+            ref = F.leaky_relu(F.conv3d(x, m.weight, None, stride=2, padding=1), 0.2)
+    assert y.shape == ref.shape and (y - ref).abs().max().item() <= _tol() * ref.abs().max().item()
+    xg = x.clone().requires_grad_(True)                      # and under autograd (WGAN-GP feeds a leaf that needs grad)
+    yg = m(xg)
+    assert "ConvForward" in type(yg.grad_fn).__name__
+    (gx,) = torch.autograd.grad(yg.sum(), xg)
+    with fp32_reference():
+        (rx,) = torch.autograd.grad(m(xg).sum(), xg)
+    assert (gx - rx).abs().max().item() <= 4e-3 * rx.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(64, 64, (1, 4, 32, 32)), (1, 64, (2, 4, 32, 64))])
+def test_gradient_penalty_double_backward_vs_cudnn(cin, cout, shape):
+    """WGAN-GP's penalty (wgangp.py:144-164) through the custom forward / _ConvInputGrad nodes against plain autograd"""
+    torch.manual_seed(cin + 31)
+    b, d, h, w = shape
+    m = nets.Conv3d(cin, cout, 4, 2, 1, bias=False).to(DEV)
+    x = torch.rand(b, cin, d, h, w, device=DEV, requires_grad=True)
+    proj = torch.randn(1, cout, d // 2, h // 2, w // 2, device=DEV)
+
+    def penalty():
+        out = (F.leaky_relu(m(x), 0.2) * proj).sum()
+        (gx,) = torch.autograd.grad(out, x, create_graph=True)
+        return ((gx.reshape(b, -1).norm(2, dim=1) - 1) ** 2).mean()
+    pen = penalty()
+    (gw,) = torch.autograd.grad(pen, m.weight)
+    with fp32_reference():
+        ref = penalty()
+        (rw,) = torch.autograd.grad(ref, m.weight)
+    assert abs(pen.item() - ref.item()) <= 2e-2 * max(1e-3, abs(ref.item()))
+    assert (gw - rw).abs().max().item() <= 2e-2 * rw.abs().max().item()
