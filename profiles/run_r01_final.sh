@@ -16,4 +16,6 @@ NCU=1 ncu --profile-from-start off --set full --clock-control none --import-sour
 python profiles/unet_breakdown.py > gpurun_out/unet_breakdown_r01_final.json 2>/dev/null
 python profiles/microbench_conv.py > gpurun_out/microbench_conv_r01_final.json 2>/dev/null
 python profiles/net_breakdown.py > gpurun_out/net_breakdown_r01.json 2>/dev/null
+python profiles/bench_train_unet.py > gpurun_out/train_unet_r01.json 2>/dev/null
+python profiles/bench_train_ddp.py > gpurun_out/train_n1_custom.json 2>/dev/null
 tail -3 gpurun_out/pytest_gpu.txt; cat gpurun_out/bench_r01.json
