@@ -55,3 +55,48 @@ def test_cpu_tensors_are_refused():
         nndistance(torch.zeros(1, 4, 3), torch.zeros(1, 5, 3))
     with pytest.raises((RuntimeError, AssertionError)):
         Camera_back_projection_layer()(torch.zeros(1, 1, 8, 8))
+
+
+def _d(v=4096):
+    """a fake, 16-byte aligned device address: argument checks come before any launch and never dereference it"""
+    return ctypes.c_void_p(v)
+
+
+@pytest.mark.parametrize("call,code,needle", [
+    # convolution entry points: shape support is part of the contract (include/genre_b200.h)
+    (lambda L: L.genre_b200_convt3d_s2_forward(_d(), 2, None, 0, 1, 2, 16, 24, _d(), 8, 32, 1, _d(), _d(), 1.0, _d(), 5, None),
+     -1, b"width"),
+    (lambda L: L.genre_b200_convt3d_s2_forward(_d(), 3, None, 0, 1, 2, 16, 16, _d(), 8, 32, 1, _d(), _d(), 1.0, _d(), 5, None),
+     -1, b"even"),
+    (lambda L: L.genre_b200_convt3d_s2_forward(_d(), 2, None, 0, 1, 2, 16, 16, _d(), 6, 32, 1, _d(), _d(), 1.0, _d(), 5, None),
+     -1, b"kernel size"),
+    (lambda L: L.genre_b200_convt3d_s2_forward(_d(4100), 2, None, 0, 1, 2, 16, 16, _d(), 8, 32, 1, _d(), _d(), 1.0, _d(), 5, None),
+     -3, b"aligned"),
+    (lambda L: L.genre_b200_convt3d_s2_merged_forward(_d(), 2, None, 0, 1, 2, 16, 16, _d(), 8, 64, 1, _d(), _d(), 1.0, _d(), 5, None),
+     -1, b"npad"),
+    (lambda L: L.genre_b200_conv3d_k8s2_s4d_forward(_d(), 2, 1, 2, 16, 24, _d(), 160, 1, _d(), _d(), 1.0, _d(), 5, None),
+     -1, b"extent"),
+    (lambda L: L.genre_b200_conv3d_k4s2_forward(_d(), 3, 1, 1, 2, 16, 16, _d(), 64, 1, _d(), _d(), 1.0, _d(), 16, None),
+     -1, b"even"),
+    (lambda L: L.genre_b200_convt_c1_tc_forward(_d(), 2, None, 0, 1, 2, 16, 48, _d(), 1, _d(), 0, _d(), None), -1, b"width"),
+    (lambda L: L.genre_b200_convt_c1_forward(_d(), 2, None, 0, 1, 2, 16, 18, _d(), 0.0, 0, _d(), None), -1, b"extent"),
+    # layout converters
+    (lambda L: L.genre_b200_ncdhw_to_blocked(_d(), 1, 6, 2, 4, 4, 0, 4, 0, _d(), None), -1, b"multiple"),
+    (lambda L: L.genre_b200_ncdhw_to_blocked(_d(), 1, 4, 2, 4, 4, 0, 5, 0, _d(), None), -1, b"group"),
+    (lambda L: L.genre_b200_ncdhw_to_blocked(_d(), 1, 2, 3, 4, 4, 1, 4, 0, _d(), None), -1, b"odd"),
+    (lambda L: L.genre_b200_blocked_to_ncdhw(_d(), 2, 1, 9, 2, 4, 4, _d(), None), -1, b"shape"),
+    (lambda L: L.genre_b200_scale_clamp_strided(_d(), 2, 6, 1.0, 0.0, 1.0, _d(), 8, None), -1, b"multiples of 4"),
+    # training kernels
+    (lambda L: L.genre_b200_convt_c1_wgrad(_d(), _d(), 1, 80, 2, 8, 8, _d(), _d(), 1 << 30, None), -1, b"Cin"),
+    (lambda L: L.genre_b200_convt_c1_wgrad(_d(), _d(), 1, 40, 2, 8, 8, _d(), _d(), 16, None), -2, b"workspace"),
+    (lambda L: L.genre_b200_conv_k8s2_wgrad(_d(), _d(), 1, 3, 20, 2, 16, 16, _d(), _d(), 1 << 30, None), -1, b"Cin"),
+    # fused glue
+    (lambda L: L.genre_b200_render_spherical_forward_pre(_d(), 1, 16, _d(), 8, 16, _d(), 50.0, 1.0, 0.0, _d(), None), -1, b"clamp"),
+])
+def test_conv_and_layout_entry_points_validate_before_launching(call, code, needle):
+    """every unsupported shape / misaligned buffer is an argument error with a message, reported without touching a GPU"""
+    lib = _lib.load()
+    rc = call(lib)
+    msg = lib.genre_b200_last_error()
+    assert rc == code, (rc, msg)
+    assert needle.lower() in msg.lower(), msg

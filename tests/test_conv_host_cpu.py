@@ -196,3 +196,62 @@ def test_pack_conv_k4s2_s2d_weights_few_input_channels():
         assert xb.shape[1] == cpad // g
         y = _taps_gemm(xb, 2, wp, 1, 1, 1)[..., :cout].permute(0, 4, 1, 2, 3)
         assert torch.allclose(y, ref, atol=1e-5)
+
+
+def test_tf32_split_is_exact_and_rounds_to_nearest():
+    """3xTF32 operand split on the host side (weights): hi has a 10-bit mantissa (ties away, like cvt.rna.tf32.f32), hi + lo
+    reproduces the fp32 value exactly, and |lo| <= 2^-11 |x|"""
+    import numpy as np
+    torch.manual_seed(15)
+    w = torch.cat((torch.randn(4096) * 3.0, torch.randn(4096) * 1e-3, torch.tensor([0.0, -0.0, 1.0, -1.0, 1.00048828125])))
+    hi = ops_conv._tf32_hi(w)
+    lo = w - hi
+    assert torch.equal(hi + lo, w)
+    assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0)                       # low 13 mantissa bits cleared
+    assert torch.all(lo.abs() <= w.abs() * 2.0 ** -11 + 1e-45)
+    # against an independent numpy emulation of round-to-nearest-ties-away at 10 mantissa bits
+    x = w.numpy().astype(np.float64)
+    m, e = np.frexp(x)                                                           # x = m * 2^e, 0.5 <= |m| < 1
+    ref = np.ldexp(np.sign(m) * np.floor(np.abs(m) * 2048 + 0.5) / 2048, e)
+    assert np.array_equal(hi.numpy().astype(np.float64), ref)
+
+
+def test_fused_sequential_is_a_plain_sequential_on_cpu_and_keeps_state_dict_keys():
+    import networks.networks as nets
+    torch.manual_seed(16)
+    dec = nets.VoxelDecoder(n_dims=8, nf=32)
+    assert isinstance(dec.main, nets.FusedSequential)
+    keys = [k for k in dec.state_dict() if k.endswith("weight") and "main." in k]
+    assert keys[0] == "main.0.weight" and "main.8.weight" in keys and "main.17.weight" in keys
+    x = torch.randn(2, 8)
+    dec.eval()
+    with torch.no_grad():
+        y = dec(x)
+        z = x.view(2, -1, 1, 1, 1)
+        for m in dec.main:                                   # module-by-module walk = what nn.Sequential does
+            z = m(z)
+    assert torch.equal(y, z)
+
+
+def test_blocked_twin_cache_semantics_on_cpu():
+    x = torch.randn(2, 8, 3, 4, 4)
+    y = ops_conv.from_blocked(ops_conv.to_blocked(x, 4), 2, 8)
+    assert torch.equal(y, x) and ops_conv._has_blocked(y)
+    assert ops_conv._blocked_f32(y) is ops_conv._cached_blocked(y)
+    y.add_(1.0)                                              # in-place update: the twin is stale and must be ignored
+    assert not ops_conv._has_blocked(y)
+    assert torch.equal(ops_conv.from_blocked(ops_conv._blocked_f32(y), 2, 8), y)
+    act = ops_conv.BlockedActivation(ops_conv.to_blocked(x, 4), 2, 8)
+    assert tuple(act.shape) == (2, 8, 3, 4, 4) and act.dim() == 5 and act.size(1) == 8 and not act.requires_grad
+    assert torch.equal(act.ncdhw(), x)
+
+
+def test_operand_mode_follows_the_cudnn_tf32_switch():
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        assert ops_conv._mode() == ops_conv.PRECISION and ops_conv._group() == (8 if ops_conv.PRECISION == "f16" else 4)
+        torch.backends.cudnn.allow_tf32 = False
+        assert ops_conv._mode() == "fp32x3" and ops_conv._x3() and ops_conv._group() == 4
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
