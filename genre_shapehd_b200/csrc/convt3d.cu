@@ -557,7 +557,7 @@ extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const v
 // genre_b200_convt3d_s2_forward except
 //   wpack [2 z-parity][4 z-tap][Cin chunk][5*5 union taps][2][npad/8][8][g], npad = 4 * cpad columns ordered
 //         n = (py*2+px)*cpad + co  (ops_conv.pack_convt_merged_weights);  scale, shift [cpad].
-// Supported: ksize 8, npad = 80 (Cout <= 20), W in {16, 32}, H % 16 == 0.
+// Supported: ksize 8, npad = 80 (Cout <= 20), W = 16 or a multiple of 32, H % 16 == 0.
 extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
                                                     int64_t D, int64_t H, int64_t W, const void *wpack_, int ksize,
                                                     int npad, int f16, const float *scale, const float *shift,
@@ -567,7 +567,8 @@ extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, 
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "convt3d_merged: null pointer");
   GB_REQUIRE(ksize == 8, GENRE_B200_EINVAL, "convt3d_merged: kernel size %d unsupported (8)", ksize);
   GB_REQUIRE(npad == 80, GENRE_B200_EINVAL, "convt3d_merged: npad %d unsupported (80 = 4 classes x 20 channels)", npad);
-  GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "convt3d_merged: input width %lld unsupported (16 or 32)", (long long)W);
+  GB_REQUIRE(W == 16 || (W > 0 && W % 32 == 0), GENRE_B200_EINVAL,
+             "convt3d_merged: input width %lld unsupported (16, or a multiple of 32 walked in 32-wide tiles)", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt3d_merged: bad extent");
   GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
              "convt3d_merged: channel groups (%d + %d) must be even in total", cg0, cg1);
@@ -586,7 +587,7 @@ extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, 
     p.base[par] = (par + pad - k0) / 2;
   }
   cudaStream_t st = as_stream(stream);
-  if (W == 32) return launch_convt_merged<4, 5, 80, 4>(p, st);
+  if (W % 32 == 0) return launch_convt_merged<4, 5, 80, 4>(p, st);  // 32-wide x tiles
   return launch_convt_merged<4, 5, 80, 2>(p, st);
 }
 
@@ -658,7 +659,7 @@ extern "C" int genre_b200_convt_c1_tc_forward(const void *src0_, int cg0, const 
 // A strided Conv3d reaches this form through space-to-depth (genre_shapehd_b200/ops_conv.py): Unet_3D.enc1 =
 // Conv3d(2 -> 20, k=8, s=2, p=3) (networks/networks.py:151) is a 5-tap stride-1 convolution over the 16 s2d channels.
 //   wpack [T z-tap][C/8 chunk][T*T taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4]
-// Supported: T in {3, 5}, W in {16, 32, 64}, H % 16 == 0, npad = 32 (or 64 with T = 3).
+// Supported: T in {3, 5}, W in {16, 32, 64}, H % 16 == 0, npad = 32 (or 64 with T = 3, 96 with T = 5).
 extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const void *src1_, int cg1, int64_t B,
                                               int64_t D, int64_t H, int64_t W, const void *wpack_, int taps, int base,
                                               int npad, int f16, const float *scale, const float *shift, float slope,
@@ -667,7 +668,8 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   g_conv_f16 = f16 != 0;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_taps: null pointer");
   GB_REQUIRE(taps == 3 || taps == 5, GENRE_B200_EINVAL, "conv3d_taps: %d taps unsupported (3 or 5)", taps);
-  GB_REQUIRE(npad == 32 || (npad == 64 && taps == 3), GENRE_B200_EINVAL, "conv3d_taps: npad %d unsupported (32; 64 with 3 taps)", npad);
+  GB_REQUIRE(npad == 32 || (npad == 64 && taps == 3) || (npad == 96 && taps == 5), GENRE_B200_EINVAL,
+             "conv3d_taps: npad %d unsupported (32; 64 with 3 taps; 96 with 5 taps)", npad);
   GB_REQUIRE(W == 16 || W == 32 || W == 64, GENRE_B200_EINVAL, "conv3d_taps: width %lld unsupported", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "conv3d_taps: bad extent");
   GB_REQUIRE(cg0 > 0 && cg1 >= 0 && (cg0 + cg1) % CT_KCG == 0 && (cg1 == 0 || src1), GENRE_B200_EINVAL,
@@ -688,6 +690,12 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
   if (taps == 3 && npad == 64) {
     if (W % 32 == 0) return launch_convt<3, 64, 4, false>(p, st);
     return launch_convt<3, 64, 2, false>(p, st);
+  }
+  // 5 taps, N = 96: Conv3d(20 -> 80, k8, s2, p3) over the 2x space-to-depth input = the input gradient of Unet_3D.dec5
+  // (ConvTranspose3d 80 -> 20); 32- or 16-wide tiles (384 / 192 TMEM columns)
+  if (taps == 5 && npad == 96) {
+    if (W % 32 == 0) return launch_convt<5, 96, 4, false>(p, st);
+    return launch_convt<5, 96, 2, false>(p, st);
   }
 #define GB_CV(TT, MM) return launch_convt<TT, 32, MM, false>(p, st)
   if (taps == 5 && W == 64) GB_CV(5, 8);

@@ -58,12 +58,28 @@ S4D_SPLIT_Z = os.environ.get("GENRE_B200_S4D_SPLIT_Z", "0") != "0"   # measured:
 EXACT_WHEN_TF32_OFF = os.environ.get("GENRE_B200_CONV_EXACT", "1") != "0"
 
 
+_FORCED_MODE = None   # set by _forced_mode(): gradient convolutions use TF32 operands (fp16 would flush small gradients)
+
+
+class _forced_mode:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        global _FORCED_MODE
+        self.old, _FORCED_MODE = _FORCED_MODE, self.mode
+
+    def __exit__(self, *exc):
+        global _FORCED_MODE
+        _FORCED_MODE = self.old
+
+
 def _mode():
     """operand mode of the next launch: 'f16' | 'tf32' (single pass, 10-bit operand mantissa = what cuDNN itself does
     while torch.backends.cudnn.allow_tf32 is on) or 'fp32x3' (fp32-accurate) when it is off or asked for explicitly"""
     if not torch.backends.cudnn.allow_tf32:
         return "fp32x3"
-    return PRECISION
+    return _FORCED_MODE or PRECISION
 
 
 def _f16():
@@ -664,6 +680,68 @@ class _ConvInputGrad(torch.autograd.Function):
         return g_gy, g_w, None, None
 
 
+# Input gradients of the two k=8 layers of Unet_3D on the tensor cores (first-order backward only).  OFF by default:
+# written at the end of round 1 without a GPU left to run them on; the formulation and the weight mapping are tested on
+# CPU (tests/test_conv_host_cpu.py), the kernel instances (5-tap N=96, merged ConvT over 32-wide x tiles) are not yet.
+TC_BACKWARD = os.environ.get("GENRE_B200_CONV_TC_BACKWARD", "0") != "0"
+
+
+def dgrad_convt_k8s2(gy, m):
+    """Input gradient of ConvTranspose3d(Cin -> Cout, k8, s2, p3) (Unet_3D.dec5, networks.py:166): out[2i-3+k] += x[i] W[ci,co,k]
+    =>  dx[ci, i] = sum_{co,k} gy[co, 2i - 3 + k] W[ci, co, k] = Conv3d(Cout -> Cin, k8, s2, p3) of gy with the SAME weight
+    tensor read as [out = Cin, in = Cout, 8, 8, 8]: the 5-tap form over the 2x space-to-depth of gy (kernel MODE 1, N = 96)."""
+    cin_t, cout_t = m.in_channels, m.out_channels
+    b, _, d, h, w = gy.shape
+    if not (gy.is_cuda and gy.dtype == torch.float32 and cin_t <= 96 and (cout_t * 8) % 8 == 0 and d % 2 == 0 and h % 32 == 0
+            and (w // 2) in (16, 32, 64)):
+        return None
+    with torch.no_grad(), _forced_mode("tf32"):
+        g = _group()
+        wpack = _pack(m, ("dgrad_k8s2", 96, g), lambda wt: pack_conv_k8s2_weights(wt, 96, g), 1)
+        xb = space_to_depth_blocked(gy.contiguous(), g)
+        if _x3():
+            xb = _split3(xb)
+        bd, cg, hh, ww, _ = xb.shape
+        cgo = (cin_t + 3) // 4
+        one = m.__dict__.get("_gb_dgrad_affine")
+        if one is None or one[0].device != gy.device:
+            one = m.__dict__["_gb_dgrad_affine"] = (torch.ones(96, device=gy.device), torch.zeros(96, device=gy.device))
+        out = torch.empty((bd, cgo, hh, ww, 4), device=gy.device, dtype=torch.float32)
+        _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg, None, 0, b, bd // b, hh, ww, wpack.data_ptr(), 5, 2, 96,
+                  0, one[0].data_ptr(), one[1].data_ptr(), 1.0, out.data_ptr(), cgo, _lib.stream_ptr(gy))
+        dx = from_blocked(out, b, cin_t)
+        dx.__dict__.pop("_gb_blocked", None)
+        return dx
+
+
+def dgrad_conv_k8s2(gy, m):
+    """Input gradient of Conv3d(Cin -> Cout, k8, s2, p3) with Cin <= 20 (Unet_3D.enc1, networks.py:151) = ConvTranspose3d(Cout ->
+    Cin, k8, s2, p3) of gy with the SAME weight tensor read as [in = Cout, out = Cin, 8, 8, 8]: the merged-parity kernel
+    (MODE 2) over 32-wide x tiles.  Cout is zero-padded to a multiple of 8 (whole K chunks)."""
+    cin, cout = m.in_channels, m.out_channels
+    b, _, d, h, w = gy.shape
+    if not (gy.is_cuda and gy.dtype == torch.float32 and cin <= 20 and h % 16 == 0 and (w == 16 or w % 32 == 0)):
+        return None
+    pad = (-cout) % 8
+    with torch.no_grad(), _forced_mode("tf32"):
+        g = _group()
+        wpack = _pack(m, ("dgrad_convt_merged", 20, g, pad),
+                      lambda wt: pack_convt_merged_weights(torch.nn.functional.pad(wt, (0, 0) * 4 + (0, pad)), 20, g), 2)
+        gyp = torch.nn.functional.pad(gy, (0, 0) * 3 + (0, pad)) if pad else gy
+        src, _ = _x3_operands(to_blocked(gyp.contiguous(), g), None)
+        bd, cg, hh, ww, _ = src.shape
+        cgo = (cin + 3) // 4
+        one = m.__dict__.get("_gb_dgrad_affine")
+        if one is None or one[0].device != gy.device:
+            one = m.__dict__["_gb_dgrad_affine"] = (torch.ones(96, device=gy.device), torch.zeros(96, device=gy.device))
+        out = torch.empty((bd * 2, cgo, 2 * hh, 2 * ww, 4), device=gy.device, dtype=torch.float32)
+        _lib.call("genre_b200_convt3d_s2_merged_forward", src.data_ptr(), cg, None, 0, b, bd // b, hh, ww, wpack.data_ptr(), 8, 80,
+                  0, one[0].data_ptr(), one[1].data_ptr(), 1.0, out.data_ptr(), cgo, _lib.stream_ptr(gy))
+        dx = from_blocked(out, b, cin)
+        dx.__dict__.pop("_gb_blocked", None)
+        return dx
+
+
 class _ConvForward(torch.autograd.Function):
     """Training: the FORWARD of a convolution on the custom kernel (conv + bias only; BatchNorm with batch statistics and
     the activation stay torch modules), the backward on cuDNN through aten::convolution_backward.  The forward is where
@@ -705,6 +783,12 @@ class _ConvForward(torch.autograd.Function):
             mask[1] = False
         gx = gw = gb = None
         gx_custom = None
+        if (TC_BACKWARD and mask[0] and not torch.is_grad_enabled() and ctx.module is not None
+                and tuple(weight.shape[2:]) == (8, 8, 8) and stride == (2, 2, 2) and padding == (3, 3, 3) and groups == 1
+                and dilation == (1, 1, 1) and out_pad == (0, 0, 0)):
+            gx_custom = (dgrad_convt_k8s2 if transposed else dgrad_conv_k8s2)(gy, ctx.module)
+            if gx_custom is not None:
+                mask[0] = False
         if mask[0] and torch.is_grad_enabled() and not transposed and ctx.module is not None:
             gx_custom = _ConvInputGrad.apply(gy, weight, x, ctx.module)   # double backward stays on the custom forward
             mask[0] = False

@@ -192,7 +192,8 @@ int genre_b200_convt3d_s2_forward(const void *src0, int cg0, const void *src1, i
  * Replaces the cuDNN call behind nn.Conv3d of Unet_3D.enc1 (networks/networks.py:151,197: Conv3d(2->20, k=8, s=2, p=3))
  * after a space-to-depth of the input (k=8/s=2 over C channels == 5 taps/s=1 over 8C channels).
  *   wpack [taps][C/8][taps*taps][2][npad/8][8][4];  out [B*D][cgo][H][W][4];  W in {16,32,64}, H % 16 == 0, npad = 32
- *   (npad = 64 with 3 taps: Conv3d(1 -> 64, k4, s2, p1) over the 2x space-to-depth input, VoxelDiscriminator main.0) */
+ *   (npad = 64 with 3 taps: Conv3d(1 -> 64, k4, s2, p1) over the 2x space-to-depth input, VoxelDiscriminator main.0;
+ *    npad = 96 with 5 taps: Conv3d(20 -> 80, k8, s2, p3) = the input gradient of Unet_3D.dec5) */
 int genre_b200_conv3d_taps_forward(const void *src0, int cg0, const void *src1, int cg1,
                                    int64_t B, int64_t D, int64_t H, int64_t W,
                                    const void *wpack, int taps, int base, int npad, int f16,

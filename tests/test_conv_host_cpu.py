@@ -255,3 +255,39 @@ def test_operand_mode_follows_the_cudnn_tf32_switch():
         assert ops_conv._mode() == "fp32x3" and ops_conv._x3() and ops_conv._group() == 4
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_input_gradients_of_the_k8_layers_as_forward_convolutions():
+    """ops_conv.dgrad_convt_k8s2 / dgrad_conv_k8s2 (GENRE_B200_CONV_TC_BACKWARD, off by default): the formulation and the
+    weight mapping, emulated on CPU: dgrad of ConvT(k8,s2,p3) = Conv3d of gy with the same weight tensor through the 5-tap
+    space-to-depth packer (N = 96 form); dgrad of Conv3d(k8,s2,p3) = ConvT of gy through the merged-parity packer with
+    the output-channel axis zero-padded to whole K chunks"""
+    torch.manual_seed(17)
+    # (1) ConvTranspose3d(6 -> 5): dx = conv3d(gy, W as [out=6, in=5])
+    w = torch.randn(6, 5, 8, 8, 8)
+    x = torch.randn(2, 6, 2, 3, 4, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose3d(x, w.double(), stride=2, padding=3)
+    gy = torch.randn_like(y)
+    (ref,) = torch.autograd.grad(y, x, gy)
+    wp = ops_conv.pack_conv_k8s2_weights(w, 8, 4)                     # conv weight [Cout=6, Cin=5], npad 8
+    gb = ops_conv.space_to_depth_blocked(gy.float(), 4)
+    dx = _taps_gemm(gb, 2, wp, 2, 2, 2)[..., :6].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(dx, ref, atol=1e-4)
+    # (2) Conv3d(2 -> 5): dx = conv_transpose3d(gy, W as [in=5 (padded to 8), out=2]) through the merged packer
+    wc = torch.randn(5, 2, 8, 8, 8)
+    x = torch.randn(1, 2, 4, 6, 8, dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(x, wc.double(), stride=2, padding=3)
+    gy = torch.randn_like(y)
+    (ref,) = torch.autograd.grad(y, x, gy)
+    pad = (-5) % 8
+    wp = ops_conv.pack_convt_merged_weights(F.pad(wc, (0, 0) * 4 + (0, pad)), 4, 4)     # [2 pz][4][chunk][25]...
+    gb = ops_conv.to_blocked(F.pad(gy.float(), (0, 0) * 3 + (0, pad)), 4)
+    out = torch.zeros_like(ref)
+    base = [1, 2]                                                                       # k = 8: (p + 3 - (p + 3) % 2) / 2
+    for pz in (0, 1):
+        yz = _taps_gemm(gb, 1, wp[pz], base[pz], 2, 2)
+        for py in (0, 1):
+            for px in (0, 1):
+                c0 = (py * 2 + px) * 4
+                out[:, :, pz::2, py::2, px::2] = yz[..., c0:c0 + 2].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(out, ref, atol=1e-4)

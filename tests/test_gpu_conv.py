@@ -461,3 +461,20 @@ def test_gradient_penalty_double_backward_vs_cudnn(cin, cout, shape):
         (rw,) = torch.autograd.grad(ref, m.weight)
     assert abs(pen.item() - ref.item()) <= 2e-2 * max(1e-3, abs(ref.item()))
     assert (gw - rw).abs().max().item() <= 2e-2 * rw.abs().max().item()
+
+
+@pytest.mark.skipif(not ops_conv.TC_BACKWARD, reason="tensor-core input gradients are opt-in (GENRE_B200_CONV_TC_BACKWARD=1): "
+                    "written after the round's GPU budget was spent, to be validated next round")
+@pytest.mark.parametrize("kind,cin,cout,shape", [("convt", 80, 20, (1, 2, 32, 32)), ("conv", 2, 20, (1, 4, 64, 64))])
+def test_tensor_core_input_gradients_of_the_k8_layers(kind, cin, cout, shape):
+    torch.manual_seed(cin)
+    b, d, h, w = shape
+    m = (nets.ConvTranspose3d(cin, cout, 8, 2, 3) if kind == "convt" else nets.Conv3d(cin, cout, 8, 2, 3)).to(DEV)
+    x = torch.randn(b, cin, d, h, w, device=DEV, requires_grad=True)
+    with fp32_reference():
+        y = m(x)
+        gy = torch.randn_like(y)
+        (ref,) = torch.autograd.grad(y, x, gy)
+    dx = (ops_conv.dgrad_convt_k8s2 if kind == "convt" else ops_conv.dgrad_conv_k8s2)(gy, m)
+    assert dx is not None and dx.shape == ref.shape
+    assert (dx - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
