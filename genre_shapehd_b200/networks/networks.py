@@ -58,6 +58,11 @@ class FusedSequential(nn.Sequential):
                     if y is not None:
                         x, i = y, j + 1
                         continue
+                    if ops_conv.BN_TRAIN and bn is not None and bn.training:
+                        z = ops_conv.bn_act_train(m(x), bn, act)          # conv module, then BN+act in one op
+                        if z is not None:
+                            x, i = z, j + 1
+                            continue
             x = m(x)
             i += 1
         return x
@@ -214,6 +219,10 @@ class Conv3d_block(nn.Module):
 
     def forward(self, x):
         y = ops_conv.conv3d(x, self.net[0], self.net[1], self.net[2].negative_slope) if x.is_cuda else None
+        if y is None and ops_conv.BN_TRAIN and x.is_cuda and self.net[1].training:
+            c = self.net[0](x)
+            z = ops_conv.bn_act_train(c, self.net[1], self.net[2])
+            return z if z is not None else self.net[2](self.net[1](c))
         return y if y is not None else self.net(x)
 
 
@@ -238,6 +247,10 @@ class Deconv3d_skip(nn.Module):
             return y
         if isinstance(x, ops_conv.BlockedActivation):
             x = x.ncdhw()
+        if ops_conv.BN_TRAIN and x.is_cuda and isinstance(self.net, nn.Sequential) and self.net[1].training:
+            c = self.net[0](cat((x, skip_in), dim=1))
+            z = ops_conv.bn_act_train(c, self.net[1], self.net[2])
+            return z if z is not None else self.net[2](self.net[1](c))
         return self.net(cat((x, skip_in), dim=1))
 
 

@@ -1016,6 +1016,68 @@ def conv_transpose3d(x, m, bn=None, slope=None):
     return None if y is None else from_blocked(y, x.shape[0], m.out_channels)
 
 
+# ---- BatchNorm3d with batch statistics + activation, training mode (csrc/bn_train.cu) --------------------------------
+# OFF by default: written at the end of round 1 without a GPU left to run it on (GENRE_B200_BN_TRAIN=1 to try it).
+BN_TRAIN = os.environ.get("GENRE_B200_BN_TRAIN", "0") != "0"
+
+
+class _BnActTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, slope):
+        x = x.contiguous()
+        b, c = x.shape[0], x.shape[1]
+        sp = x.numel() // (b * c)
+        y = torch.empty_like(x)
+        mean, invstd = torch.empty(c, device=x.device), torch.empty(c, device=x.device)
+        nbytes = _lib.load().genre_b200_bn_workspace_bytes(c)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        track = bn.track_running_stats and bn.running_mean is not None
+        _lib.call("genre_b200_bn_act_train_forward", x.data_ptr(), b, c, sp, gamma.data_ptr() if gamma is not None else None,
+                  beta.data_ptr() if beta is not None else None, bn.running_mean.data_ptr() if track else None,
+                  bn.running_var.data_ptr() if track else None, float(bn.eps), float(bn.momentum), float(slope), y.data_ptr(),
+                  mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr(x))
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(x, gamma, beta, mean, invstd)
+        ctx.slope = float(slope)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, gamma, beta, mean, invstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        b, c = x.shape[0], x.shape[1]
+        sp = x.numel() // (b * c)
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(c, device=x.device) if gamma is not None else None
+        dbeta = torch.empty(c, device=x.device) if beta is not None else None
+        nbytes = _lib.load().genre_b200_bn_workspace_bytes(c)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.call("genre_b200_bn_act_train_backward", x.data_ptr(), dy.data_ptr(), b, c, sp,
+                  gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None, mean.data_ptr(),
+                  invstd.data_ptr(), ctx.slope, dx.data_ptr(), dgamma.data_ptr() if dgamma is not None else None,
+                  dbeta.data_ptr() if dbeta is not None else None, ws.data_ptr(), nbytes, _lib.stream_ptr(x))
+        return dx, dgamma, dbeta, None, None
+
+
+def bn_act_train(x, bn, act=None):
+    """act(bn(x)) with batch statistics as 3 streaming kernels forward / 2 backward, or None when not applicable"""
+    if not (BN_TRAIN and ENABLED and isinstance(bn, torch.nn.BatchNorm3d) and bn.training and bn.momentum is not None
+            and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+            and (x.numel() // (x.shape[0] * x.shape[1])) % 4 == 0):
+        return None
+    if act is None:
+        slope = 1.0
+    elif isinstance(act, torch.nn.ReLU):
+        slope = 0.0
+    elif isinstance(act, torch.nn.LeakyReLU):
+        slope = float(act.negative_slope)
+    else:
+        return None
+    return _BnActTrain.apply(x, bn.weight, bn.bias, bn, slope)
+
+
 def gemm_conv(x, m):
     """A ConvTranspose3d(k, s=1, p=0) on a 1^3 input IS a plain matrix product,
           out[b, co, :] = sum_ci x[b, ci] * W[ci, co, :]   =   x[B,Cin] @ W[Cin, Cout*k^3],

@@ -266,6 +266,23 @@ int genre_b200_conv_k8s2_wgrad(const float *x, const float *gy, int64_t B, int64
                                int64_t D, int64_t H, int64_t W, float *dW,
                                void *workspace, size_t workspace_bytes, void *stream);
 
+/* BatchNorm3d with BATCH statistics (training) fused with its ReLU / LeakyReLU, forward and backward, NCDHW fp32:
+ * nn.BatchNorm3d + nn.LeakyReLU of Conv3d_block / Deconv3d_skip (networks/networks.py:193-222) and the BatchNorm3d + ReLU of
+ * the decoders' stacks (:40-57) while training (cuDNN: 5.3 ms of a 22 ms Unet_3D step for ~0.3 ms worth of HBM traffic).
+ * x, y, dy, dx [B][C][S] contiguous and 16-byte aligned, S = D*H*W a multiple of 4; gamma / beta / running_* [C] or NULL;
+ * slope: 1 = no activation, 0 = ReLU; two-pass variance, fixed-order reductions (bitwise reproducible).
+ * OPT-IN (GENRE_B200_BN_TRAIN=1): written after round 1's GPU budget was spent, not yet run on a GPU. */
+size_t genre_b200_bn_workspace_bytes(int64_t C);
+int genre_b200_bn_act_train_forward(const float *x, int64_t B, int64_t C, int64_t S,
+                                    const float *gamma, const float *beta, float *running_mean, float *running_var,
+                                    float eps, float momentum, float slope,
+                                    float *y, float *save_mean, float *save_invstd,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+int genre_b200_bn_act_train_backward(const float *x, const float *dy, int64_t B, int64_t C, int64_t S,
+                                     const float *gamma, const float *beta, const float *save_mean, const float *save_invstd,
+                                     float slope, float *dx, float *dgamma, float *dbeta,
+                                     void *workspace, size_t workspace_bytes, void *stream);
+
 /* Layout boundary of the convolution kernels: contiguous NCDHW fp32 (what networks/networks.py's modules exchange,
  * e.g. Unet_3D.forward networks.py:170-190) <-> channel-blocked [B*D][C/g][H][W][g] (16 bytes per unit).
  *   mode 0: plain;  mode 1: space-to-depth, channel = ((c*2+pz)*2+py)*2+px (Conv3d k8 s2, Unet_3D.enc1; with cpad > 8C the

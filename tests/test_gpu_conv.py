@@ -478,3 +478,29 @@ def test_tensor_core_input_gradients_of_the_k8_layers(kind, cin, cout, shape):
     dx = (ops_conv.dgrad_convt_k8s2 if kind == "convt" else ops_conv.dgrad_conv_k8s2)(gy, m)
     assert dx is not None and dx.shape == ref.shape
     assert (dx - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+@pytest.mark.skipif(not ops_conv.BN_TRAIN, reason="fused training BatchNorm is opt-in (GENRE_B200_BN_TRAIN=1): written after the "
+                    "round's GPU budget was spent, to be validated next round")
+@pytest.mark.parametrize("act", [None, "relu", "leaky"])
+@pytest.mark.parametrize("shape", [(4, 20, 8, 16, 16), (2, 5, 3, 4, 4), (3, 64, 4, 8, 8)])
+def test_bn_act_train_forward_backward_vs_torch(shape, act):
+    torch.manual_seed(shape[1])
+    bn, ref_bn = torch.nn.BatchNorm3d(shape[1]).to(DEV).train(), torch.nn.BatchNorm3d(shape[1]).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+        ref_bn.load_state_dict(bn.state_dict())
+    a = {None: None, "relu": torch.nn.ReLU(), "leaky": torch.nn.LeakyReLU(0.01)}[act]
+    x = (torch.randn(*shape, device=DEV) * 2 + 0.7).requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    y = ops_conv.bn_act_train(x, bn, a)
+    assert y is not None
+    yr = ref_bn(xr) if a is None else a(ref_bn(xr))
+    g = torch.randn_like(yr)
+    y.backward(g); yr.backward(g)
+    assert (y - yr).abs().max().item() <= 1e-4 * max(1.0, yr.abs().max().item())
+    assert (x.grad - xr.grad).abs().max().item() <= 1e-4 * max(1.0, xr.grad.abs().max().item())
+    assert (bn.weight.grad - ref_bn.weight.grad).abs().max().item() <= 1e-3 * max(1.0, ref_bn.weight.grad.abs().max().item())
+    assert (bn.bias.grad - ref_bn.bias.grad).abs().max().item() <= 1e-3 * max(1.0, ref_bn.bias.grad.abs().max().item())
+    assert torch.allclose(bn.running_mean, ref_bn.running_mean, atol=1e-5) and torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-4)
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
