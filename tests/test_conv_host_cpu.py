@@ -291,3 +291,42 @@ def test_input_gradients_of_the_k8_layers_as_forward_convolutions():
                 c0 = (py * 2 + px) * 4
                 out[:, :, pz::2, py::2, px::2] = yz[..., c0:c0 + 2].permute(0, 4, 1, 2, 3)
     assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_weight_gradient_formulas_of_the_fp32_pipe_kernels():
+    """The index arithmetic csrc/convt_c1_wgrad.cu implements, written out with slices and checked against autograd:
+         ConvT(Cin -> 1, k4, s2, p1):  dW[ci, k] = sum_{b,i} x[b,ci,i] * gy[b, 2i - 1 + k]    dx[b,ci,i] = sum_k W[ci,k] gy[b, 2i - 1 + k]
+         Conv3d(Cin -> Cout, k8, s2, p3): dW[co, ci, k] = sum_{b,o} gy[b,co,o] * x[b,ci, 2o - 3 + k]"""
+    torch.manual_seed(18)
+    # --- ConvTranspose3d(3 -> 1, k4, s2, p1)
+    w = torch.randn(3, 1, 4, 4, 4, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(2, 3, 2, 3, 4, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose3d(x, w, stride=2, padding=1)
+    gy = torch.randn_like(y)
+    rx, rw = torch.autograd.grad(y, (x, w), gy)
+    gp = F.pad(gy[:, 0], (1, 2, 1, 2, 1, 2))                      # index 2i - 1 + k + 1 >= 0, up to 2(n-1) + 3
+    d, h, wd = x.shape[2:]
+    dw = torch.zeros(3, 4, 4, 4, dtype=torch.float64)
+    dx = torch.zeros_like(x)
+    for kz in range(4):
+        for ky in range(4):
+            for kx in range(4):
+                g = gp[:, kz:kz + 2 * d:2, ky:ky + 2 * h:2, kx:kx + 2 * wd:2]          # gy[b, 2i - 1 + k]
+                dw[:, kz, ky, kx] = (x.detach() * g[:, None]).sum((0, 2, 3, 4))
+                dx += w.detach()[None, :, 0, kz, ky, kx, None, None, None] * g[:, None]
+    assert torch.allclose(dw, rw[:, 0], atol=1e-10) and torch.allclose(dx, rx, atol=1e-10)
+    # --- Conv3d(2 -> 3, k8, s2, p3)
+    wc = torch.randn(3, 2, 8, 8, 8, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(2, 2, 4, 6, 8, dtype=torch.float64)
+    y = F.conv3d(x, wc, stride=2, padding=3)
+    gy = torch.randn_like(y)
+    (rw,) = torch.autograd.grad(y, wc, gy)
+    xp = F.pad(x, (3, 4, 3, 4, 3, 4))                             # index 2o - 3 + k + 3 >= 0, up to 2(n/2 - 1) + 7
+    do, ho, wo = gy.shape[2:]
+    dw = torch.zeros_like(rw)
+    for kz in range(8):
+        for ky in range(8):
+            for kx in range(8):
+                xs = xp[:, :, kz:kz + 2 * do:2, ky:ky + 2 * ho:2, kx:kx + 2 * wo:2]    # x[b, ci, 2o - 3 + k]
+                dw[:, :, kz, ky, kx] = torch.einsum("bozyx,bizyx->oi", gy, xs)
+    assert torch.allclose(dw, rw, atol=1e-9)
