@@ -126,10 +126,13 @@ def run_reference(args):
     from oracle import oracle
     oracle.lib()
     cores = os.cpu_count() or 1
-    threads = min(cores, args.batch)
-    depth = bench_depth_batch(args.batch)
-    # each step = a bounded sample of the workload: `sample` maps of the 32-map batch
-    sample = args.batch
+    threads = max(1, min(cores, 256))            # every host thread: maps are independent, one map per thread at a time
+    import numpy as np
+    batch = bench_depth_batch(args.batch)
+    # each step = a bounded sample of the workload: whole 32-map batches, as many as it takes to occupy every thread once
+    n_batches = max(1, -(-threads // args.batch))
+    depth = np.ascontiguousarray(np.tile(batch, (n_batches, 1, 1, 1)))
+    sample = depth.shape[0]
     cpu_forward_batch(oracle, depth[:2], 1)  # touch pages
     t = time.time()
     cpu_forward_batch(oracle, depth[:sample], threads)
@@ -137,7 +140,7 @@ def run_reference(args):
     budget = 90.0
     steps, warmup = args.steps, args.warmup
     if per_batch * (steps + warmup) > budget:  # keep the whole run within a few minutes
-        sample = max(threads, int(sample * budget / (per_batch * (steps + warmup))))
+        sample = max(min(threads, sample), int(sample * budget / (per_batch * (steps + warmup))))
     for _ in range(warmup):
         cpu_forward_batch(oracle, depth[:sample], threads)
     t0 = time.time()
@@ -148,9 +151,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d of the %d maps of one batch per step, %d threads over maps "
-                                       "(oracle/genre_oracle.c; the reference op has no CPU implementation)" % (sample, args.batch, threads)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(threads, sample), "kind": "port",
+                             "sample": "%d maps per step (the %d-map batch repeated), %d threads over maps, host has %d logical CPUs "
+                                       "(oracle/genre_oracle.c; the reference op has no CPU implementation)"
+                                       % (sample, args.batch, min(threads, sample), cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

@@ -20,7 +20,8 @@ def test_reference_arm_prints_one_contract_line():
     assert d["unit"] == "shapes/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and "cam_bp" in d["metric"]
     assert "256x256" in d["config"]["workload"] and d["config"]["batch_per_gpu"] == 32 and d["config"]["voxel_res"] == 128
-    assert d["value"] > 0 and abs(d["value"] - 32 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    maps_per_step = d["value"] * d["ms_per_step"] * 1e-3                 # whole maps, at least one per thread
+    assert d["value"] > 0 and maps_per_step >= 1 and abs(maps_per_step - round(maps_per_step)) <= 1e-6 * maps_per_step
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
