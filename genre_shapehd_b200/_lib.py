@@ -132,6 +132,10 @@ def call(name, *args):
 
 
 def stream_ptr(t):
+    """the current stream of the tensor's device; the kernels launch on the CURRENT device, so it must be the tensor's"""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("genre_shapehd_b200: tensor on %s but the current CUDA device is %d; wrap the call in "
+                           "`with torch.cuda.device(tensor.device):`" % (t.device, torch.cuda.current_device()))
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

@@ -38,12 +38,28 @@ def _unavailable(what):
     return f
 
 
+def find_reference():
+    """the frozen callers: $GENRE_REF, else the staged copy <repo>/baseline/_ref (travels to the GPU box), else /root/reference"""
+    for root in (os.environ.get("GENRE_REF"), os.path.join(genre_shapehd_b200.REPO_ROOT, "baseline", "_ref"), "/root/reference"):
+        if root and os.path.isdir(os.path.join(root, "models")):
+            return root
+    return None
+
+
 def bootstrap(reference_root=None, offline_resnet=True):
-    root = reference_root or os.environ.get("GENRE_REF") or "/root/reference"
-    if not os.path.isdir(os.path.join(root, "models")):
-        raise FileNotFoundError("no GenRe-ShapeHD checkout at %r" % root)
-    os.environ.setdefault("GENRE_REF", root)
+    root = reference_root or find_reference()
+    if root is None or not os.path.isdir(os.path.join(root, "models")):
+        raise FileNotFoundError("no GenRe-ShapeHD checkout at %r (searched $GENRE_REF, <repo>/baseline/_ref, /root/reference; "
+                                "`python -c 'import __graft_entry__ as g; g.build()'` stages baseline/_ref)" % root)
+    os.environ["GENRE_REF"] = root
     genre_shapehd_b200.install(root)
+    stub_optional_modules(offline_resnet)
+    return root
+
+
+def stub_optional_modules(offline_resnet=True):
+    """stand-ins for skimage / trimesh (imported at module level by the frozen files, unused on the differentiable path) and
+    an offline torchvision resnet18"""
     sk = _stub("skimage")
     if getattr(sk, "__genre_b200_stub__", False):
         measure = _stub("skimage.measure", marching_cubes_lewiner=_unavailable("skimage.measure.marching_cubes"),
@@ -70,4 +86,3 @@ def bootstrap(reference_root=None, offline_resnet=True):
                 tvr.resnet18 = resnet18
             except Exception:
                 pass
-    return root

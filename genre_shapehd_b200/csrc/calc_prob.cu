@@ -122,10 +122,11 @@ calc_prob_backward_kernel(const float *__restrict__ prob, const float *__restric
     float total;
     const float after = carry + warp_excl_suffix_sum(a0 + ww[0], total);
     float o[4];
-    o[0] = ww[0] / pv[0] - (after + a0) / (1.0f - pv[0]);
-    o[1] = ww[1] / pv[1] - (after + a1) / (1.0f - pv[1]);
-    o[2] = ww[2] / pv[2] - (after + a2) / (1.0f - pv[2]);
-    o[3] = ww[3] / pv[3] - (after + a3) / (1.0f - pv[3]);
+    // the second term vanishes when nothing follows (the ray's last sample: calc_prob_kernel.cu:169-172 takes head = w/p there);
+    // skipping it when the suffix sum is exactly 0 keeps p == 1 at such a sample finite (0/0 otherwise)
+    const float sfx[4] = {after + a0, after + a1, after + a2, after + a3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = ww[i] / pv[i] - (sfx[i] != 0.0f ? sfx[i] / (1.0f - pv[i]) : 0.0f);
     if (VEC) {
       if (z < Z) *reinterpret_cast<float4 *>(g + z) = make_float4(o[0], o[1], o[2], o[3]);
     } else {

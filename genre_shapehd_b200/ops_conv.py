@@ -42,10 +42,16 @@ _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
 C1_MAX_CIN = 48
 K4S2_MIN_CIN = 8
-# Operand type of the tensor-core kernels: "f16" (default) = fp16 operands, fp32 accumulation: the same 10-bit
-# mantissa as TF32 with half the operand bytes (the kernels are bound by shared-memory operand bandwidth, so ~2x
-# faster); "tf32" = fp32 storage read as TF32.  Both accumulate in fp32 and produce fp32 activations.
-PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "f16")
+# Operand mode of the tensor-core kernels (GENRE_B200_CONV_PRECISION, or `with ops_conv.precision(mode):`):
+#   "exact" (DEFAULT)  fp32-accurate: the reference's fp32 semantics (north_star: occupancies within 1e-4).  Implemented by
+#                      EXACT_IMPL: "f16x2" = fp16 hi/lo operand split, 2 MMAs per K step, separate accumulators for the
+#                      hi*hi and the cross terms; "fp32x3" = 3xTF32 with the three products along K (3 MMAs per K=8 step)
+#   "f16"              single pass, fp16 operands (10-bit mantissa, 5-bit exponent), fp32 accumulation: opt-in, tested at
+#                      4e-3 * max|ref| per layer; inputs beyond fp16's range are the caller's responsibility
+#   "tf32"             single pass, TF32 operands (what cuDNN does while torch.backends.cudnn.allow_tf32 is on)
+# torch.backends.cudnn.allow_tf32 = False upgrades a single-pass mode to "exact" (PyTorch's own switch for fp32 convolutions).
+PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "exact")
+EXACT_IMPL = os.environ.get("GENRE_B200_CONV_EXACT_IMPL", "fp32x3")
 # k=8 ConvTranspose3d with Cout <= 20 (Unet_3D.dec5): merge the four (y,x) parity classes into one N=80 MMA stream
 MERGE_PARITIES = os.environ.get("GENRE_B200_CONV_MERGE", "1") != "0"
 # Unet_3D.enc1 (4x space-to-depth form): z class on blockIdx.y (N = 80, two CTAs per SM) instead of all 8 classes in N = 160
@@ -59,9 +65,13 @@ EXACT_WHEN_TF32_OFF = os.environ.get("GENRE_B200_CONV_EXACT", "1") != "0"
 
 
 _FORCED_MODE = None   # set by _forced_mode(): gradient convolutions use TF32 operands (fp16 would flush small gradients)
+_OVERRIDE = None      # set by precision()
+_EXACT = ("exact", "fp32x3", "f16x2")
 
 
 class _forced_mode:
+    """internal: single-pass operand type of the convolutions issued inside (never downgrades an exact mode)"""
+
     def __init__(self, mode):
         self.mode = mode
 
@@ -74,12 +84,36 @@ class _forced_mode:
         _FORCED_MODE = self.old
 
 
+class precision:
+    """public: `with ops_conv.precision("f16"):` selects the operand mode of the custom convolutions issued inside"""
+
+    def __init__(self, mode):
+        if mode not in ("exact", "f16", "tf32", "fp32x3", "f16x2"):
+            raise ValueError("unknown conv precision %r" % (mode,))
+        self.mode = mode
+
+    def __enter__(self):
+        global _OVERRIDE
+        self.old, _OVERRIDE = _OVERRIDE, self.mode
+
+    def __exit__(self, *exc):
+        global _OVERRIDE
+        _OVERRIDE = self.old
+
+
 def _mode():
-    """operand mode of the next launch: 'f16' | 'tf32' (single pass, 10-bit operand mantissa = what cuDNN itself does
-    while torch.backends.cudnn.allow_tf32 is on) or 'fp32x3' (fp32-accurate) when it is off or asked for explicitly"""
-    if not torch.backends.cudnn.allow_tf32:
-        return "fp32x3"
-    return _FORCED_MODE or PRECISION
+    """operand mode of the next launch: 'f16' | 'tf32' (single pass) or the fp32-accurate 'fp32x3' | 'f16x2'"""
+    base = _OVERRIDE or PRECISION
+    if base in _EXACT or not torch.backends.cudnn.allow_tf32:
+        return EXACT_IMPL if base not in ("fp32x3", "f16x2") else base
+    return _FORCED_MODE or base
+
+
+def describe_mode():
+    m = _mode()
+    return {"f16": "f16 single pass (10-bit operand mantissa, fp32 accumulate)", "tf32": "tf32 single pass (10-bit operand mantissa)",
+            "fp32x3": "exact: 3xTF32 operand split (fp32-accurate, tested <= 1e-4)",
+            "f16x2": "exact: fp16 hi/lo operand split, 2 MMAs per K step (fp32-accurate, tested <= 1e-4)"}[m]
 
 
 def _f16():
@@ -670,7 +704,10 @@ class _ConvInputGrad(torch.autograd.Function):
         ggx = ggx.contiguous()
         g_gy = g_w = None
         if ctx.needs_input_grad[0]:
-            g_gy = conv3d(ggx, m)                      # no grad mode here: the custom forward kernel (bias is not part of it)
+            # no grad mode here: the custom forward kernel (bias is not part of it).  Grad-of-grads of a penalty are ~1e-4..1e-7:
+            # never fp16 operands (subnormal / flushed), TF32 at least (the exact modes stay exact)
+            with _forced_mode("tf32"):
+                g_gy = conv3d(ggx, m)
             if g_gy is None:
                 g_gy = torch.nn.functional.conv3d(ggx, weight, None, m.stride, m.padding, m.dilation, m.groups)
             elif m.bias is not None:
@@ -997,7 +1034,7 @@ def conv_transpose3d(x, m, bn=None, slope=None):
     """ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> ReLU / LeakyReLU(slope)]; None if not covered
     (the caller then runs the plain modules)."""
     if x.is_cuda and not isinstance(x, BlockedActivation) and _needs_grad(x, m.weight, m.bias):
-        if bn is not None or slope is not None:
+        if bn is not None or slope is not None or x.dim() != 5:
             return None
         if TRAIN_FORWARD and _convt_c1_train_supported(x, m):
             return _ConvTC1Train.apply(x, m.weight, m.bias, m)

@@ -1,110 +1,164 @@
 #!/usr/bin/env python
 """BASELINE configs[3] (ShapeHD fine-tune step and 3D-WGAN-GP critic step, batch 8 per GPU, DDP over NCCL) on the
-networks drop-in.  The 2D ImageEncoder (ResNet-18) is outside the hot path and not available on the GPU box, so the
-decoder is fed random 200-d codes directly; everything 3D is the reference's graph:
-  shapehd step : models/shapehd.py:67-79,113-118  VoxelDecoder -> sigmoid -> frozen D; loss = BCE + w * -mean(D(.))
-  wgangp D step: models/wgangp.py:77-142,144-164  D(real), D(G(z)) and the gradient penalty (double backward through D),
-                 accumulated with no_sync() so the three backward() calls cost one all-reduce
-Under autograd the covered layers run their forward on the custom kernels and their backward on cuDNN / the custom
-weight-gradient kernels (ops_conv._ConvForward, _ConvTC1Train); GENRE_B200_CONV_TRAIN_FORWARD=0 gives the all-cuDNN step.
-NCU=shapehd|wgan: run one warm step of that kind between cudaProfilerStart/Stop (for `ncu --profile-from-start off`).
-
+networks drop-in, driven through the reference's FROZEN classes (baseline/_ref):
+  shapehd step : models/shapehd.py Net (:82-118: two marrnet2 = ImageEncoder -> VoxelDecoder, frozen D) + the loss of
+                 :67-79 (BCE-with-logits + w * -mean(D(sigmoid(voxel)))) + Adam on marrnet2 (:42-47)
+  wgangp D step: models/wgangp.py:77-112,144-164 restated on its own D / G classes (:193-214): D(real), D(G(z)) and the
+                 gradient penalty (double backward through D), accumulated under no_sync() so that the three backward()
+                 calls cost ONE all-reduce
+run() is imported by bench.py (the `secondary_ddp` block of every --gpus N line); stand-alone:
     torchrun --nproc-per-node N profiles/bench_train_ddp.py [--steps K]          # one JSON line from rank 0
+Reports per step: ms (max over ranks), shapes/s, and the all-reduce time that backward does NOT hide = step time with
+gradient sync minus the same step under no_sync() (no collective issued).
+NCU=shapehd|wgan: run one warm step of that kind between cudaProfilerStart/Stop (for `ncu --profile-from-start off`).
 """
-import argparse, contextlib, json, os, sys, time
+import argparse
+import contextlib
+import json
+import os
+import sys
+import types
+
 import torch
-import torch.nn as nn
 import torch.nn.functional as F
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, REPO)
-import genre_shapehd_b200
-genre_shapehd_b200.install()
-from genre_shapehd_b200 import dist_util
-import networks.networks as nets
-from torch.nn.parallel import DistributedDataParallel as DDP
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--warmup", type=int, default=3)
-ap.add_argument("--batch", type=int, default=8)
-args = ap.parse_args()
-world, rank, local = dist_util.env_world()
-torch.cuda.set_device(local)
-dev = torch.device("cuda", local)
-dist_util.init("nccl", dev)
-torch.manual_seed(1 + rank)
-B = args.batch
-wrap = (lambda m: DDP(m, device_ids=[local])) if world > 1 else (lambda m: m)
 
-# ---- ShapeHD fine-tune step ---------------------------------------------------------------------------------------
-dec = wrap(nets.VoxelDecoder().to(dev))
-D_frozen = nets.VoxelDiscriminator().to(dev).eval()
-for p in D_frozen.parameters():
-    p.requires_grad_(False)
-opt = torch.optim.Adam(dec.parameters(), lr=1e-3)
-codes = torch.randn(B, 200, device=dev)
-target = (torch.rand(B, 1, 128, 128, 128, device=dev) < 0.05).float()
+def run(dev, world, rank, local, batch=8, steps=6, warmup=3, which=("shapehd", "wgan")):
+    from genre_shapehd_b200 import compat, dist_util, ops_conv
+    compat.bootstrap()
+    import models.shapehd as shd
+    import models.wgangp as wg
+    from torch.nn.parallel import DistributedDataParallel as DDP
 
-def shapehd_step():
-    opt.zero_grad(set_to_none=True)
-    logits = dec(codes)
-    loss = F.binary_cross_entropy_with_logits(logits, target) - 1e-3 * D_frozen(torch.sigmoid(logits)).mean()
-    loss.backward()
-    opt.step()
-    return loss
+    torch.manual_seed(1 + rank)
+    B = batch
+    res = {"n_gpus": world, "batch_per_gpu": B, "steps": steps, "conv_mode": ops_conv.describe_mode(),
+           "bn_train_custom": ops_conv.BN_TRAIN, "tc_backward": ops_conv.TC_BACKWARD,
+           "workload": "BASELINE configs[3]: frozen models/shapehd.py Net + loss, and models/wgangp.py critic step, DDP over NCCL"}
 
-# ---- WGAN-GP critic step ---------------------------------------------------------------------------------------------
-G = nets.VoxelGenerator().to(dev)
-Dn = wrap(nets.VoxelDiscriminator().to(dev))
-opt_d = torch.optim.Adam(Dn.parameters(), lr=1e-4, betas=(0.5, 0.9))
-real = target
-noise = torch.randn(B, 200, 1, 1, 1, device=dev)
+    def wrap(m):
+        return DDP(m, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else m
 
-def wgan_d_step():
-    opt_d.zero_grad(set_to_none=True)
-    nosync = Dn.no_sync if world > 1 else contextlib.nullcontext
-    with nosync():
-        (-Dn(real).mean()).backward()
-        with torch.no_grad():
-            fake = G(noise)
-        Dn(fake).mean().backward()
-    eps = torch.rand(B, 1, 1, 1, 1, device=dev)
-    inter = (eps * real + (1 - eps) * fake).requires_grad_(True)
-    out = Dn(inter)
-    grad, = torch.autograd.grad(out.sum(), inter, create_graph=True)
-    gp = 10.0 * ((grad.reshape(B, -1).norm(2, dim=1) - 1) ** 2).mean()
-    gp.backward()
-    opt_d.step()
-    return gp
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        dist_util.barrier(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        dist_util.barrier(dev)
+        return dist_util.max_over_ranks(e0.elapsed_time(e1), dev) / steps, float(last)
 
-def bench(fn):
-    for _ in range(args.warmup):
+    target = (torch.rand(B, 1, 128, 128, 128, device=dev) < 0.05).float()
+
+    # ---- ShapeHD fine-tune step ---------------------------------------------------------------------------------------
+    if "shapehd" in which:
+        net = shd.Net().to(dev)
+        net.train()
+        ddp = wrap(net)
+        opt = torch.optim.Adam(net.marrnet2.parameters(), lr=1e-3)
+        depth, normal = torch.rand(B, 1, 256, 256, device=dev), torch.rand(B, 3, 256, 256, device=dev)
+        silhou = (torch.rand(B, 1, 256, 256, device=dev) > 0.4).float()
+
+        def shapehd_step(sync=True):
+            opt.zero_grad(set_to_none=True)
+            ctx = contextlib.nullcontext() if (sync or world == 1) else ddp.no_sync()
+            with ctx:
+                pred = ddp(types.SimpleNamespace(depth=depth.clone(), normal=normal.clone(), silhou=silhou))
+                loss = F.binary_cross_entropy_with_logits(pred["voxel"], target) + 1e-3 * (-pred["is_real"].mean())
+                loss.backward()
+            opt.step()
+            return loss.detach()
+        if os.environ.get("NCU") == "shapehd":
+            return _ncu(shapehd_step)
+        ms, loss = timed(shapehd_step)
+        res["shapehd"] = {"step_ms": ms, "shapes_per_s": world * B / ms * 1e3, "loss_finite": bool(loss == loss)}
+        if world > 1:
+            ms_ns, _ = timed(lambda: shapehd_step(sync=False))
+            res["shapehd"].update({"step_ms_no_sync": ms_ns, "exposed_allreduce_ms": max(0.0, ms - ms_ns),
+                                   "exposed_allreduce_frac": max(0.0, ms - ms_ns) / ms,
+                                   "allreduce_bytes": 4 * sum(p.numel() for p in net.marrnet2.parameters())})
+        del net, ddp, opt
+
+    # ---- WGAN-GP critic step ---------------------------------------------------------------------------------------------
+    if "wgan" in which:
+        G = wg.G(200).to(dev)
+        G.noise = G.noise.to(dev)
+        Dn = wg.D().to(dev)
+        for p in G.parameters():
+            p.requires_grad = False
+        ddp_d = wrap(Dn)
+        opt_d = torch.optim.Adam(Dn.parameters(), lr=1e-4, betas=(0.5, 0.9))
+        real = target
+        lam, norm = 10.0, 1.0
+
+        def wgan_d_step(sync=True):
+            opt_d.zero_grad(set_to_none=True)
+            nosync = ddp_d.no_sync if world > 1 else contextlib.nullcontext
+            with nosync():
+                ddp_d(real).mean().backward(torch.tensor(-1.0, device=dev))          # wgangp.py:94-95
+                with torch.no_grad():
+                    _, fake = G(B)
+                ddp_d(fake).mean().backward(torch.tensor(1.0, device=dev))           # :100-103
+            with (nosync() if not sync else contextlib.nullcontext()):
+                alpha = torch.rand(B, 1, 1, 1, 1, device=dev)                         # :144-164
+                inter = (alpha * real + (1 - alpha) * fake).requires_grad_(True)
+                out = ddp_d(inter)
+                grads, = torch.autograd.grad(outputs=out, inputs=inter, grad_outputs=torch.ones_like(out), create_graph=True,
+                                             retain_graph=True, only_inputs=True)
+                gp = (((grads.view(B, -1) + 1e-16).norm(2, dim=1) - norm) ** 2).mean() * lam
+                gp.backward()
+            opt_d.step()
+            return gp.detach()
+        if os.environ.get("NCU") == "wgan":
+            return _ncu(wgan_d_step)
+        ms, gp = timed(wgan_d_step)
+        res["wgangp_critic"] = {"step_ms": ms, "shapes_per_s": world * B / ms * 1e3, "gp_finite": bool(gp == gp)}
+        if world > 1:
+            ms_ns, _ = timed(lambda: wgan_d_step(sync=False))
+            res["wgangp_critic"].update({"step_ms_no_sync": ms_ns, "exposed_allreduce_ms": max(0.0, ms - ms_ns),
+                                         "exposed_allreduce_frac": max(0.0, ms - ms_ns) / ms,
+                                         "allreduce_bytes": 4 * sum(p.numel() for p in Dn.parameters())})
+    return res
+
+
+def _ncu(fn):
+    for _ in range(2):
         fn()
-    dist_util.barrier(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        last = fn()
-    e1.record()
-    dist_util.barrier(dev)
-    ms = dist_util.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
-    return ms, float(last)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    return None
 
-if os.environ.get("NCU"):
-    fn = shapehd_step if os.environ["NCU"] == "shapehd" else wgan_d_step
-    for _ in range(2): fn()
-    torch.cuda.synchronize(); torch.cuda.profiler.start(); fn(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
-    sys.exit(0)
-from genre_shapehd_b200 import ops_conv
-res = {"n_gpus": world, "batch_per_gpu": B, "steps": args.steps, "train_forward_custom": ops_conv.TRAIN_FORWARD}
-ms, loss = bench(shapehd_step)
-res["shapehd_step_ms"] = ms
-res["shapehd_shapes_per_s"] = world * B / ms * 1e3
-res["shapehd_loss_finite"] = bool(loss == loss)
-ms, gp = bench(wgan_d_step)
-res["wgangp_d_step_ms"] = ms
-res["wgangp_shapes_per_s"] = world * B / ms * 1e3
-res["wgangp_gp_finite"] = bool(gp == gp)
-if rank == 0:
-    print(json.dumps(res), flush=True)
-dist_util.finalize()
+
+def main():
+    import genre_shapehd_b200
+    genre_shapehd_b200.install()
+    from genre_shapehd_b200 import dist_util
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--which", default="shapehd,wgan")
+    args = ap.parse_args()
+    world, rank, local = dist_util.env_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_util.init("nccl", dev)
+    res = run(dev, world, rank, local, args.batch, args.steps, args.warmup, tuple(args.which.split(",")))
+    if rank == 0 and res is not None:
+        print(json.dumps(res), flush=True)
+    dist_util.finalize()
+
+
+if __name__ == "__main__":
+    main()

@@ -167,19 +167,20 @@ def test_pack_plans_reproduce_the_packers():
     """ops_conv._pack repacks through a gather index derived from the packer once per layer: same bytes as the packer"""
     import torch.nn as nn
     torch.manual_seed(12)
-    m = nn.ConvTranspose3d(16, 5, 8, 2, 3)
-    for g in (4, 8):
-        direct = ops_conv.pack_convt_merged_weights(m.weight.detach(), 8, g)
-        via_plan = ops_conv._pack(m, ("convt_merged", 8, g), lambda wt: ops_conv.pack_convt_merged_weights(wt, 8, g), 2, half=(g == 8))
-        assert via_plan.dtype == direct.dtype and torch.equal(via_plan, direct)
-    c = nn.Conv3d(5, 6, 4, 2, 1)
-    direct = ops_conv.pack_conv_k4s2_weights(c.weight.detach(), 8, 8, 4)
-    via_plan = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
-    assert torch.equal(via_plan, direct)
-    with torch.no_grad():
-        c.weight.mul_(2.0)                                   # in-place update (optimizer step): the cache must follow
-    again = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
-    assert torch.equal(again, direct * 2)
+    with ops_conv.precision("tf32"):      # single-pass packing (the exact modes pack hi/lo parts: tested separately)
+        m = nn.ConvTranspose3d(16, 5, 8, 2, 3)
+        for g in (4, 8):
+            direct = ops_conv.pack_convt_merged_weights(m.weight.detach(), 8, g)
+            via_plan = ops_conv._pack(m, ("convt_merged", 8, g), lambda wt: ops_conv.pack_convt_merged_weights(wt, 8, g), 2, half=(g == 8))
+            assert via_plan.dtype == direct.dtype and torch.equal(via_plan, direct)
+        c = nn.Conv3d(5, 6, 4, 2, 1)
+        direct = ops_conv.pack_conv_k4s2_weights(c.weight.detach(), 8, 8, 4)
+        via_plan = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
+        assert torch.equal(via_plan, direct)
+        with torch.no_grad():
+            c.weight.mul_(2.0)                                   # in-place update (optimizer step): the cache must follow
+        again = ops_conv._pack(c, ("k4s2", 8, 8, 4), lambda wt: ops_conv.pack_conv_k4s2_weights(wt, 8, 8, 4), 1, half=False)
+        assert torch.equal(again, direct * 2)
 
 
 def test_pack_conv_k4s2_s2d_weights_few_input_channels():
@@ -246,15 +247,31 @@ def test_blocked_twin_cache_semantics_on_cpu():
     assert torch.equal(act.ncdhw(), x)
 
 
-def test_operand_mode_follows_the_cudnn_tf32_switch():
-    old = torch.backends.cudnn.allow_tf32
+def test_operand_mode_selection():
+    """default = the fp32-accurate mode; single-pass modes are opt-in and torch.backends.cudnn.allow_tf32 = False upgrades them"""
+    old, oldp = torch.backends.cudnn.allow_tf32, ops_conv.PRECISION
     try:
         torch.backends.cudnn.allow_tf32 = True
-        assert ops_conv._mode() == ops_conv.PRECISION and ops_conv._group() == (8 if ops_conv.PRECISION == "f16" else 4)
-        torch.backends.cudnn.allow_tf32 = False
-        assert ops_conv._mode() == "fp32x3" and ops_conv._x3() and ops_conv._group() == 4
+        ops_conv.PRECISION = "exact"
+        assert ops_conv._mode() == ops_conv.EXACT_IMPL and ops_conv._mode() in ("fp32x3", "f16x2")
+        with ops_conv.precision("f16"):
+            assert ops_conv._mode() == "f16" and ops_conv._group() == 8
+            with ops_conv._forced_mode("tf32"):                      # gradient convolutions: never fp16 operands
+                assert ops_conv._mode() == "tf32" and ops_conv._group() == 4
+            torch.backends.cudnn.allow_tf32 = False
+            assert ops_conv._mode() == ops_conv.EXACT_IMPL
+            torch.backends.cudnn.allow_tf32 = True
+        with ops_conv._forced_mode("tf32"):                          # ... and never a downgrade of the exact mode
+            assert ops_conv._mode() == ops_conv.EXACT_IMPL
+        with ops_conv.precision("fp32x3"):
+            assert ops_conv._mode() == "fp32x3" and ops_conv._x3() and ops_conv._group() == 4
+        ops_conv.PRECISION = "tf32"
+        assert ops_conv._mode() == "tf32"
+        with pytest.raises(ValueError):
+            ops_conv.precision("fp8")
+        assert "exact" in ops_conv.describe_mode() or "single pass" in ops_conv.describe_mode()
     finally:
-        torch.backends.cudnn.allow_tf32 = old
+        torch.backends.cudnn.allow_tf32, ops_conv.PRECISION = old, oldp
 
 
 def test_input_gradients_of_the_k8_layers_as_forward_convolutions():
