@@ -49,6 +49,8 @@ _SIGNATURES = {
     "genre_b200_convt_c1_tc_forward": [_ptr, _int, _ptr, _int, _i64, _i64, _i64, _i64, _ptr, _int, _ptr, _int, _ptr, _ptr],
     "genre_b200_blocked_f32_to_f16": [_ptr, _int, _i64, _i64, _i64, _ptr, _ptr],
     "genre_b200_render_spherical_forward_pre": [_ptr, _i64, _int, _ptr, _int, _int, _ptr, _f32, _f32, _f32, _ptr, _ptr],
+    "genre_b200_render_spherical_forward_skip": [_ptr, _i64, _int, _ptr, _int, _int, _ptr, _int, _f32, _f32, _f32, _ptr, _ptr, _size,
+                                                 _ptr],
     "genre_b200_sph_bp_forward_fused": [_ptr] + [_i64] * 8 + [_ptr] + [_i64] * 5 + [_f32, _f32, _ptr, _i64, _int, _ptr,
                                                                                        _size, _ptr],
     "genre_b200_scale_clamp_strided": [_ptr, _i64, _i64, _f32, _f32, _f32, _ptr, _i64, _ptr],
@@ -70,7 +72,7 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + [
     "genre_b200_last_error", "genre_b200_version", "genre_b200_voxelize_workspace_bytes",
     "genre_b200_convt_c1_wgrad_workspace_bytes", "genre_b200_conv_k8s2_wgrad_workspace_bytes",
-    "genre_b200_bn_workspace_bytes"])
+    "genre_b200_bn_workspace_bytes", "genre_b200_render_spherical_workspace_bytes"])
 
 _lib = None
 launch_count = 0  # kernels of this library enqueued through the binding (bench.py reports it as gpu_launches)
@@ -84,7 +86,7 @@ _LAUNCHES = {
     "genre_b200_cam_bp_stage_project": 1, "genre_b200_voxelize_stage_splat": 1,
     "genre_b200_convt3d_s2_forward": 1, "genre_b200_conv3d_taps_forward": 1,
     "genre_b200_convt_c1_forward": 1, "genre_b200_conv3d_k4s2_forward": 1,
-    "genre_b200_render_spherical_forward_pre": 1, "genre_b200_sph_bp_forward_fused": 2, "genre_b200_scale_clamp_strided": 1,
+    "genre_b200_render_spherical_forward_pre": 1, "genre_b200_render_spherical_forward_skip": 2, "genre_b200_sph_bp_forward_fused": 2, "genre_b200_scale_clamp_strided": 1,
     "genre_b200_bn_act_train_forward": 3, "genre_b200_bn_act_train_backward": 2, "genre_b200_conv_k8s2_wgrad": 2, "genre_b200_convt_c1_wgrad": 2, "genre_b200_convt_c1_dgrad": 1,
     "genre_b200_blocked_split3": 1, "genre_b200_convt_c1_tc_forward": 1, "genre_b200_blocked_f32_to_f16": 1,
     "genre_b200_convt3d_s2_merged_forward": 1, "genre_b200_conv3d_k8s2_s4d_forward": 1, "genre_b200_ncdhw_to_blocked": 1, "genre_b200_blocked_to_ncdhw": 1,
@@ -116,6 +118,8 @@ def load():
     lib.genre_b200_conv_k8s2_wgrad_workspace_bytes.argtypes = []
     lib.genre_b200_bn_workspace_bytes.restype = _size
     lib.genre_b200_bn_workspace_bytes.argtypes = [_i64]
+    lib.genre_b200_render_spherical_workspace_bytes.restype = _size
+    lib.genre_b200_render_spherical_workspace_bytes.argtypes = [_i64, _int]
     _lib = lib
     return lib
 

@@ -20,7 +20,7 @@ import torch
 
 from genre_shapehd_b200 import _lib
 from toolbox.cam_bp.cam_bp.modules.camera_backprojection_module import Camera_back_projection_layer
-from toolbox.spherical_proj import gen_sph_grid, render_spherical, sph_pad
+from toolbox.spherical_proj import gen_sph_grid, render_forward, render_spherical, sph_pad
 
 
 class GenRe3DGlue(torch.nn.Module):
@@ -39,9 +39,8 @@ class GenRe3DGlue(torch.nn.Module):
         r = self.render
         n = proj.shape[0]
         sph = proj.new_empty((n, 1, r.sph_res, r.sph_res))
-        _lib.call("genre_b200_render_spherical_forward_pre", proj.data_ptr(), n, self.res, r._dirs_on(proj.device).data_ptr(),
-                  r.sph_res, r.z_res, r.depth_weight.data_ptr(), self.scale, self.lo, self.hi, sph.data_ptr(),
-                  _lib.stream_ptr(proj))
+        render_forward(proj, n, self.res, r._dirs_on(proj.device), r.sph_res, r.z_res, r.depth_weight, sph,
+                       pre=(self.scale, self.lo, self.hi))
         return proj, sph_pad(sph, self.margin)
 
     @torch.no_grad()

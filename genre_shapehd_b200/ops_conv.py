@@ -717,10 +717,10 @@ class _ConvInputGrad(torch.autograd.Function):
         return g_gy, g_w, None, None
 
 
-# Input gradients of the two k=8 layers of Unet_3D on the tensor cores (first-order backward only).  OFF by default:
-# written at the end of round 1 without a GPU left to run them on; the formulation and the weight mapping are tested on
-# CPU (tests/test_conv_host_cpu.py), the kernel instances (5-tap N=96, merged ConvT over 32-wide x tiles) are not yet.
-TC_BACKWARD = os.environ.get("GENRE_B200_CONV_TC_BACKWARD", "0") != "0"
+# Input gradients of the two k=8 layers of Unet_3D on the tensor cores (first-order backward only).  On by default since
+# round 2 (GPU-validated: tests/test_gpu_conv.py::test_tensor_core_input_gradients_of_the_k8_layers); GENRE_B200_CONV_TC_BACKWARD=0
+# hands them back to cuDNN.
+TC_BACKWARD = os.environ.get("GENRE_B200_CONV_TC_BACKWARD", "1") != "0"
 
 
 def dgrad_convt_k8s2(gy, m):
@@ -1054,8 +1054,9 @@ def conv_transpose3d(x, m, bn=None, slope=None):
 
 
 # ---- BatchNorm3d with batch statistics + activation, training mode (csrc/bn_train.cu) --------------------------------
-# OFF by default: written at the end of round 1 without a GPU left to run it on (GENRE_B200_BN_TRAIN=1 to try it).
-BN_TRAIN = os.environ.get("GENRE_B200_BN_TRAIN", "0") != "0"
+# On by default since round 2 (GPU-validated: tests/test_gpu_conv.py::test_bn_act_train_forward_backward_vs_torch);
+# GENRE_B200_BN_TRAIN=0 restores torch's BatchNorm3d kernels.
+BN_TRAIN = os.environ.get("GENRE_B200_BN_TRAIN", "1") != "0"
 
 
 class _BnActTrain(torch.autograd.Function):

@@ -44,6 +44,18 @@ def sph_pad(sph_tensor, padding_margin=16):
     return rep_padded_sph
 
 
+def render_forward(vox, n, res, dirs64, sph_res, z_res, depth_weight, out, pre=None):
+    """the fused renderer with empty-space skipping (csrc/render_sph.cu); pre = (scale, lo, hi) renders
+    clamp(vox * scale, lo, hi) without materialising it"""
+    nbytes = _lib.load().genre_b200_render_spherical_workspace_bytes(n, res)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=vox.device)
+    sc, lo, hi = pre if pre is not None else (1.0, 0.0, 0.0)
+    _lib.call("genre_b200_render_spherical_forward_skip", vox.data_ptr(), n, res, dirs64.data_ptr(), sph_res, z_res,
+              depth_weight.data_ptr(), 1 if pre is not None else 0, float(sc), float(lo), float(hi), out.data_ptr(),
+              ws.data_ptr(), nbytes, _lib.stream_ptr(vox))
+    return out
+
+
 class _RenderSpherical(Function):
     @staticmethod
     def forward(ctx, vox, dirs64, depth_weight, sph_res, z_res):
@@ -54,8 +66,7 @@ class _RenderSpherical(Function):
         vox = vox.contiguous()
         n, res = vox.size(0), vox.size(2)
         out = vox.new_empty((n, 1, sph_res, sph_res))
-        _lib.call("genre_b200_render_spherical_forward", vox.data_ptr(), n, res, dirs64.data_ptr(), sph_res, z_res,
-                  depth_weight.data_ptr(), out.data_ptr(), _lib.stream_ptr(vox))
+        render_forward(vox, n, res, dirs64, sph_res, z_res, depth_weight, out)
         ctx.save_for_backward(vox, dirs64, depth_weight)
         ctx.sph_res, ctx.z_res = sph_res, z_res
         return out

@@ -307,6 +307,19 @@ int genre_b200_render_spherical_forward_pre(const float *vox, int64_t N, int res
                                             int sph_res, int z_res, const float *depth_weight,
                                             float pre_scale, float pre_lo, float pre_hi, float *out, void *stream);
 
+/* The spherical renderer with EMPTY-SPACE SKIPPING (forward): same contract and results (within ~1e-6) as
+ * genre_b200_render_spherical_forward / _forward_pre (use_pre != 0 renders clamp(vox * pre_scale, pre_lo, pre_hi)).
+ * A pre-pass marks the 8^3 bricks that hold a voxel > 1e-5 (dilated by one voxel); along each ray, 32-sample chunks that
+ * only touch unmarked bricks (every sample clamps to p = 1e-5, spherical_proj.py:66) are advanced in closed form instead
+ * of 32 x 8 gathers.  GenRe's input is a thin shell: ~80 % of the chunks.  workspace: caller-owned,
+ * genre_b200_render_spherical_workspace_bytes(N, res) bytes (zeroed by the call).  Falls back to the plain kernels when
+ * res % 4 != 0 or z_res > 1024. */
+size_t genre_b200_render_spherical_workspace_bytes(int64_t N, int res);
+int genre_b200_render_spherical_forward_skip(const float *vox, int64_t N, int res, const double *dirs, int sph_res,
+                                             int z_res, const float *depth_weight, int use_pre, float pre_scale,
+                                             float pre_lo, float pre_hi, float *out, void *workspace,
+                                             size_t workspace_bytes, void *stream);
+
 /* Net.backproject_spherical (genre_full_model.py:134-143) in one call: radius = in_bias + in_scale * sph (the
  * `1 - crop_sph`; the crop is expressed through the strides), out = 1 - R * mean distance on hit voxels and 0
  * elsewhere (= (-tdf + 1/R) * R * clamp(cnt,0,1)), maps written out_map_stride floats apart (a channel of the

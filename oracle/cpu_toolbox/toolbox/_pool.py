@@ -8,7 +8,7 @@ _pool = None
 def pool():
     global _pool
     if _pool is None:
-        _pool = ThreadPoolExecutor(max(1, int(os.environ.get("GENRE_ORACLE_THREADS", os.cpu_count() or 1))))
+        _pool = ThreadPoolExecutor(max(1, int(os.environ.get("GENRE_ORACLE_THREADS", len(os.sched_getaffinity(0))))))
     return _pool
 
 

@@ -28,7 +28,6 @@ class render_spherical(torch.nn.Module):         # spherical_proj.py:31-72
     def __init__(self, sph_res=128, z_res=256):
         super().__init__()
         self.sph_res, self.z_res = sph_res, z_res
-        dirs = gen_sph_grid(sph_res).double().numpy().reshape(sph_res, sph_res, 1, 3)
         # same arithmetic as spherical_proj.py:39-57: fp64 table * 2 * (1 - alpha), rounded to fp32 once
         phi = np.linspace(0, 180, sph_res * 2 + 1)[1::2] * np.pi / 180
         theta = np.linspace(0, 360, sph_res + 1)[:-1] * np.pi / 180

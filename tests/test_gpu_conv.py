@@ -463,8 +463,7 @@ def test_gradient_penalty_double_backward_vs_cudnn(cin, cout, shape):
     assert (gw - rw).abs().max().item() <= 2e-2 * rw.abs().max().item()
 
 
-@pytest.mark.skipif(not ops_conv.TC_BACKWARD, reason="tensor-core input gradients are opt-in (GENRE_B200_CONV_TC_BACKWARD=1): "
-                    "written after the round's GPU budget was spent, to be validated next round")
+@pytest.mark.skipif(not ops_conv.TC_BACKWARD, reason="tensor-core input gradients switched off (GENRE_B200_CONV_TC_BACKWARD=0)")
 @pytest.mark.parametrize("kind,cin,cout,shape", [("convt", 80, 20, (1, 2, 32, 32)), ("conv", 2, 20, (1, 4, 64, 64))])
 def test_tensor_core_input_gradients_of_the_k8_layers(kind, cin, cout, shape):
     torch.manual_seed(cin)
@@ -480,8 +479,7 @@ def test_tensor_core_input_gradients_of_the_k8_layers(kind, cin, cout, shape):
     assert (dx - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
 
-@pytest.mark.skipif(not ops_conv.BN_TRAIN, reason="fused training BatchNorm is opt-in (GENRE_B200_BN_TRAIN=1): written after the "
-                    "round's GPU budget was spent, to be validated next round")
+@pytest.mark.skipif(not ops_conv.BN_TRAIN, reason="fused training BatchNorm switched off (GENRE_B200_BN_TRAIN=0)")
 @pytest.mark.parametrize("act", [None, "relu", "leaky"])
 @pytest.mark.parametrize("shape", [(4, 20, 8, 16, 16), (2, 5, 3, 4, 4), (3, 64, 4, 8, 8)])
 def test_bn_act_train_forward_backward_vs_torch(shape, act):

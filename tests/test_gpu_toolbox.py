@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from genre_shapehd_b200 import _lib
+from genre_shapehd_b200.synth import sphere_depth, uniform_depth
 from nndistance.functions.nnd import NNDFunction, nndistance, nndistance_score
 from oracle import ref_gpu
 from toolbox.calc_prob.calc_prob.functions.calc_prob import CalcStopProb
@@ -348,8 +349,10 @@ def _occupancy(n, res, seed):
     return torch.clamp(v + soft * (torch.rand(v.shape, device=DEV, generator=gen) < 0.02), 1e-5, 1 - 1e-5)
 
 
-@pytest.mark.parametrize("res,s,z", [(24, 16, 64), (32, 8, 50), (128, 128, 256)])
+@pytest.mark.parametrize("res,s,z", [(24, 16, 64), (32, 8, 50), (128, 128, 256), (40, 24, 100)])
 def test_render_spherical_fused_vs_oracle_and_unfused(oracle, res, s, z):
+    """the renderer (empty-space skipping included: res % 4 == 0 in every case) against the INDEPENDENT CPU oracle at every
+    size, full GenRe size (128^3, 128x128 rays, 256 samples) included, and against the op-by-op torch composition"""
     m = render_spherical(sph_res=s, z_res=z).to(DEV)
     n = 2
     vox = _occupancy(n, res, 1) if res >= 32 else torch.rand(n, 1, res, res, res, device=DEV)
@@ -357,9 +360,49 @@ def test_render_spherical_fused_vs_oracle_and_unfused(oracle, res, s, z):
     assert out.shape == (n, 1, s, s)
     ref = m.forward_unfused(vox)  # grid_sample(align_corners=True) + clamp + CalcStopProb + matmul + prod
     assert (out - ref).abs().max().item() < 1e-4
-    if res <= 32:
-        o = oracle.render_spherical(vox.cpu().numpy(), m.grid.cpu().numpy(), m.depth_weight.cpu().numpy())
-        np.testing.assert_allclose(out.cpu().numpy(), o, atol=2e-5)
+    o = oracle.render_spherical(vox.cpu().numpy(), m.grid.cpu().numpy(), m.depth_weight.cpu().numpy())
+    np.testing.assert_allclose(out.cpu().numpy(), o, atol=2e-5)
+
+
+@pytest.mark.parametrize("kind", ["empty", "shell", "dense", "genre", "corner_voxel", "zeros_and_negatives"])
+def test_render_spherical_skipping_equals_the_plain_kernel(kind):
+    """genre_b200_render_spherical_forward_skip against genre_b200_render_spherical_forward (no skipping) on inputs that
+    stress the occupancy logic: nothing occupied, a thin shell, everything occupied, GenRe's own clamp(cam_bp * 50) volume,
+    single voxels at brick / volume corners, and raw volumes with exact zeros and negative values"""
+    from genre_shapehd_b200 import _lib
+    from toolbox.spherical_proj import render_forward
+    res, s, z, n = 128, 128, 256, 2
+    m = render_spherical(sph_res=s, z_res=z).to(DEV)
+    if kind == "empty":
+        vox = torch.full((n, 1, res, res, res), 1e-5, device=DEV)
+    elif kind == "shell":
+        vox = _occupancy(n, res, 3)
+    elif kind == "dense":
+        vox = torch.rand(n, 1, res, res, res, device=DEV)
+    elif kind == "genre":
+        d = torch.from_numpy(np.stack([sphere_depth(radius=0.35), uniform_depth(1)])[:, None]).to(DEV)
+        vox = torch.clamp(Camera_back_projection_layer()(d) * 50, 1e-5, 1 - 1e-5)
+    elif kind == "corner_voxel":
+        vox = torch.full((n, 1, res, res, res), 1e-5, device=DEV)
+        for (x, y, zz) in [(0, 0, 0), (127, 127, 127), (7, 8, 63), (64, 64, 64), (8, 7, 120), (127, 0, 64)]:
+            vox[0, 0, x, y, zz] = 0.9
+        vox[1, 0, 56:72, 63, 64] = 0.5
+    else:
+        vox = torch.zeros(n, 1, res, res, res, device=DEV)
+        vox[0, 0, 40:50, 40:50, 40:50] = -3.0
+        vox[1, 0, 60:70, 60:70, 60:70] = 0.3
+    out = m(vox)
+    plain = torch.empty_like(out)
+    _lib.call("genre_b200_render_spherical_forward", vox.data_ptr(), n, res, m._dirs_on(vox.device).data_ptr(), s, z,
+              m.depth_weight.data_ptr(), plain.data_ptr(), _lib.stream_ptr(vox))
+    assert (out - plain).abs().max().item() <= 3e-6
+    # the pre-transform form: clamp(v * 50, 1e-5, 1 - 1e-5) applied on the fly, skipping decided on the transformed values
+    raw = vox / 50
+    a, b = torch.empty_like(out), torch.empty_like(out)
+    render_forward(raw, n, res, m._dirs_on(vox.device), s, z, m.depth_weight, a, pre=(50.0, 1e-5, 1 - 1e-5))
+    _lib.call("genre_b200_render_spherical_forward_pre", raw.data_ptr(), n, res, m._dirs_on(vox.device).data_ptr(), s, z,
+              m.depth_weight.data_ptr(), 50.0, 1e-5, 1 - 1e-5, b.data_ptr(), _lib.stream_ptr(vox))
+    assert (a - b).abs().max().item() <= 3e-6
 
 
 def test_render_spherical_backward_vs_autograd_of_the_composition():
