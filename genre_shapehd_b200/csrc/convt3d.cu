@@ -169,16 +169,35 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
 // T: taps per dimension of a parity class (K/2: 2 for k=4, 4 for k=8); NPAD: padded Cout (32 or 64); MT = W/8.
-template <int T, int NPAD, int MT>
+// X2: the fp32-accurate fp16 hi/lo operand split.  Activations arrive as [B*D][2 parts: hi, lo'][cg][H][W][8 fp16] with
+// lo' = (a - hi) * 2^11, weights as [W_hi | W_lo'] side by side along N (lo' = (w - hi) * 2^11).  Per K step and tap:
+//     A_hi  x [W_hi | W_lo']  ->  TMEM columns [0, 2*NPAD)         (one MMA, N = 2*NPAD)
+//     A_lo' x  W_hi           ->  TMEM columns [NPAD, 2*NPAD)      (one MMA, N = NPAD)
+// so the hi*hi products and the 2^11-scaled cross terms keep separate accumulators (the tensor core's fp32 accumulator
+// truncates: a step's error scales with the partial sum it joins, and the cross terms would otherwise ride on the big one),
+// and the epilogue returns acc_hi + 2^-11 * acc_cross.  2 MMAs per K step instead of the 3 of a K-expanded split.
+template <int T, int NPAD, int MT, bool X2 = false>
 struct ConvTCfg {
   static constexpr int W = 8 * MT;
   static constexpr int PY = CT_BY + T - 1, PX = W + T - 1;     // halo extent
+  static constexpr int PARTS = X2 ? 2 : 1;
+  static constexpr int NACC = PARTS * NPAD;                    // accumulator columns per M-tile = width of the B operand
   static constexpr int A_CG_BYTES = PY * PX * 16;              // one channel group of the halo = LBO of A
-  static constexpr int A_BYTES = CT_KCG * A_CG_BYTES;
-  static constexpr int B_TAP_BYTES = 2 * (NPAD / 8) * 128;     // one (y,x) tap: [2 kcore][NPAD/8][8 rows][16 B]
-  static constexpr int B_BYTES = T * T * B_TAP_BYTES;
-  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 127) / 128) * 128;
-  static constexpr int TMEM_COLS = MT * NPAD <= 32 ? 32 : MT * NPAD <= 64 ? 64 : MT * NPAD <= 128 ? 128 : MT * NPAD <= 256 ? 256 : 512;
+  static constexpr int A_BYTES = PARTS * CT_KCG * A_CG_BYTES;  // [part][channel group][halo]
+  static constexpr int B_TAP_BYTES = 2 * (NACC / 8) * 128;     // one (y,x) tap: [2 kcore][NACC/8][8 rows][16 B]
+  // A stage holds the halo of one (z tap, K chunk) and the weights of ROWS of its T tap rows; YS = T / ROWS (rounded up)
+  // stages walk the same halo when all T*T taps do not fit twice into shared memory (X2 with 5x5 union taps: 128 KB).
+  static constexpr int stage_bytes(int ys) { return ((A_BYTES + ((T + ys - 1) / ys) * T * B_TAP_BYTES + 127) / 128) * 128; }
+  static constexpr int pick_ys() {
+    for (int ys = 1; ys < T; ++ys)
+      if (2 * stage_bytes(ys) <= 218 * 1024) return ys;
+    return T;
+  }
+  static constexpr int YS = pick_ys();
+  static constexpr int ROWS = (T + YS - 1) / YS;
+  static constexpr int B_BYTES = ROWS * T * B_TAP_BYTES;
+  static constexpr int STAGE_BYTES = stage_bytes(YS);
+  static constexpr int TMEM_COLS = MT * NACC <= 32 ? 32 : MT * NACC <= 64 ? 64 : MT * NACC <= 128 ? 128 : MT * NACC <= 256 ? 256 : 512;
   // Two CTAs per SM whenever TMEM (<= 256 columns each) and shared memory (<= ~112 KB each) allow: one CTA's prologue
   // (TMEM alloc, pipeline fill) and epilogue (TMEM drain, stores) then overlap the other's MMA stream.
   static constexpr int S_ALONE = (218 * 1024) / STAGE_BYTES > 6 ? 6 : (218 * 1024) / STAGE_BYTES;
@@ -189,7 +208,8 @@ struct ConvTCfg {
   static constexpr int POS_PER_THREAD = (POS + CT_PRODUCERS - 1) / CT_PRODUCERS;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 256;
   static_assert(STAGES >= 2, "stage too large");
-  static_assert(MT * NPAD <= 512, "accumulators exceed TMEM");
+  static_assert(MT * NACC <= 512, "accumulators exceed TMEM");
+  static_assert(NACC <= 256 && NACC % 16 == 0 && NPAD % 16 == 0 || !X2, "X2: MMA N must be a multiple of 16, at most 256");
 };
 
 // MODE 0: 8 parity classes (blockIdx.y), output at 2*j + parity (ConvTranspose3d stride 2); TZ = T = K/2 taps
@@ -207,10 +227,14 @@ struct ConvTCfg {
 // MODE 4: ConvTranspose3d(k 4, s 2, p 1) to ONE output channel (the last layer of every decoder): MODE 3's geometry with
 //         N = 16 columns of which 8 are the output classes; the epilogue adds the bias (shift[0]), optionally applies
 //         the sigmoid, and writes the NCDHW fp32 volume directly.
-template <int TZ, int T, int NPAD, int MT, int MODE, bool F16>
+// OP: operand type: 0 = TF32 (fp32 storage), 1 = fp16, 2 = fp16 hi/lo split (X2, see ConvTCfg)
+template <int TZ, int T, int NPAD, int MT, int MODE, int OP>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 convt3d_s2_kernel(const ConvTParams p) {
-  using Cfg = ConvTCfg<T, NPAD, MT>;
+  constexpr bool F16 = OP != 0, X2 = OP == 2;
+  using Cfg = ConvTCfg<T, NPAD, MT, X2>;
+  constexpr int NACC = Cfg::NACC;
+  constexpr float LO_SCALE = 1.0f / 2048.0f;   // the cross-term accumulators hold 2^11 x their value
   constexpr bool PAR = MODE == 0, MERGE = MODE == 2, MERGE8 = MODE == 3, C1 = MODE == 4;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *stages = smem;
@@ -234,9 +258,11 @@ convt3d_s2_kernel(const ConvTParams p) {
   // Stage enumeration shared by the producer and the MMA issuer: q = tz * nchunk + kc, skipped when the z tap plane
   // of that K chunk lies outside the input (it contributes nothing).  The per-dimension base offset of a chunk is
   // uniform (parity class / plain convolution) or a function of the chunk's source sub-volume (strided conv).
-  auto stage_of = [&](int q, int &tz, int &kc, int &bz, int &by, int &bx) -> bool {
-    tz = q / nchunk;
-    kc = q - tz * nchunk;
+  auto stage_of = [&](int q, int &tz, int &kc, int &ys, int &bz, int &by, int &bx) -> bool {
+    ys = q % Cfg::YS;
+    const int qq = q / Cfg::YS;
+    tz = qq / nchunk;
+    kc = qq - tz * nchunk;
     if (p.srcpar_cgs) {
       const int sv = ((kc * CT_KCG) / p.srcpar_cgs) & 7;  // & 7: the K range may hold several blocks of 8 sub-volumes (3xTF32)
       bz = 1 - ((sv >> 2) & 1);
@@ -250,7 +276,7 @@ convt3d_s2_kernel(const ConvTParams p) {
     const int zi = zj + bz - tz;
     return zi >= 0 && zi < p.D;
   };
-  const int n_q = TZ * nchunk;
+  const int n_q = TZ * nchunk * Cfg::YS;
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -294,32 +320,40 @@ convt3d_s2_kernel(const ConvTParams p) {
       ++it;
     };
     for (int q = 0; q < n_q; ++q) {
-      int tz, kc, bz, by, bx;
-      if (!stage_of(q, tz, kc, bz, by, bx)) continue;
+      int tz, kc, ys, bz, by, bx;
+      if (!stage_of(q, tz, kc, ys, bz, by, bx)) continue;
       const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
       uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
       if (tid == 0) {
-        const float *wsrc = p.wpack + ((((size_t)par * TZ + tz) * nchunk + kc) * (size_t)(Cfg::B_BYTES / 4));
-        mbar_arrive_expect_tx(&full[s], Cfg::B_BYTES);
-        bulk_g2s(sa + Cfg::A_BYTES, wsrc, Cfg::B_BYTES, &full[s]);
+        // weights of tap rows [ys*ROWS, ...) of this (class, z tap, K chunk): a contiguous slice of its T*T-tap block
+        const int rows = (ys + 1) * Cfg::ROWS <= T ? Cfg::ROWS : T - ys * Cfg::ROWS;
+        const uint32_t bytes = (uint32_t)(rows * T * Cfg::B_TAP_BYTES);
+        const float *wsrc = p.wpack + ((((size_t)par * TZ + tz) * nchunk + kc) * (size_t)(T * T * Cfg::B_TAP_BYTES / 4)) +
+                            (size_t)ys * Cfg::ROWS * T * (Cfg::B_TAP_BYTES / 4);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(sa + Cfg::A_BYTES, wsrc, bytes, &full[s]);
       }
       const int zi = zj + bz - tz;
       const int gy0 = y0 + by - (T - 1), gx0 = x0 + bx - (T - 1);  // halo row hy holds input row gy0 + hy
 #pragma unroll
-      for (int c = 0; c < CT_KCG; ++c) {
-        int cg = kc * CT_KCG + c;
-        const float *src = p.src0;
-        int ncg = p.cg0;
-        if (cg >= p.cg0) { cg -= p.cg0; src = p.src1; ncg = p.cg1; }
-        const float *plane = src + ((((size_t)b * p.D + zi) * ncg + cg) * p.H) * (size_t)p.W * 4;
+      for (int part = 0; part < Cfg::PARTS; ++part) {
 #pragma unroll
-        for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
-          if (hoff[i] < 0) continue;
-          const int gy = gy0 + hy[i], gx = gx0 + hx[i];
-          const bool ok = (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
-          const float *g = ok ? plane + ((size_t)gy * p.W + gx) * 4 : plane;
-          cp_async16_zfill(sa + c * Cfg::A_CG_BYTES + hoff[i], g, ok);
+        for (int c = 0; c < CT_KCG; ++c) {
+          int cg = kc * CT_KCG + c;
+          const float *src = p.src0;
+          int ncg = p.cg0;
+          if (cg >= p.cg0) { cg -= p.cg0; src = p.src1; ncg = p.cg1; }
+          // X2: [B*D][part][cg][H][W][16 B]
+          const float *plane = src + (((((size_t)b * p.D + zi) * Cfg::PARTS + part) * ncg + cg) * p.H) * (size_t)p.W * 4;
+#pragma unroll
+          for (int i = 0; i < Cfg::POS_PER_THREAD; ++i) {
+            if (hoff[i] < 0) continue;
+            const int gy = gy0 + hy[i], gx = gx0 + hx[i];
+            const bool ok = (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
+            const float *g = ok ? plane + ((size_t)gy * p.W + gx) * 4 : plane;
+            cp_async16_zfill(sa + (part * CT_KCG + c) * Cfg::A_CG_BYTES + hoff[i], g, ok);
+          }
         }
       }
       publish();
@@ -340,7 +374,13 @@ convt3d_s2_kernel(const ConvTParams p) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         float v[8];
-        tmem_ld8(trow + (uint32_t)(mt * NPAD), v);
+        tmem_ld8(trow + (uint32_t)(mt * NACC), v);
+        if constexpr (X2) {
+          float l[8];
+          tmem_ld8(trow + (uint32_t)(mt * NACC + NPAD), l);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaf(l[i], LO_SCALE, v[i]);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           v[i] += bias;
@@ -370,8 +410,15 @@ convt3d_s2_kernel(const ConvTParams p) {
           for (int cgo = 0; cgo < CP / 4; ++cgo) {
             if (cgo >= p.cgo) continue;  // uniform across the CTA
             float v[8];
-            tmem_ld4x2(trow + (uint32_t)(mt * NPAD + (qzy * 2) * CP + cgo * 4),
-                       trow + (uint32_t)(mt * NPAD + (qzy * 2 + 1) * CP + cgo * 4), v);
+            tmem_ld4x2(trow + (uint32_t)(mt * NACC + (qzy * 2) * CP + cgo * 4),
+                       trow + (uint32_t)(mt * NACC + (qzy * 2 + 1) * CP + cgo * 4), v);
+            if constexpr (X2) {
+              float l[8];
+              tmem_ld4x2(trow + (uint32_t)(mt * NACC + NPAD + (qzy * 2) * CP + cgo * 4),
+                         trow + (uint32_t)(mt * NACC + NPAD + (qzy * 2 + 1) * CP + cgo * 4), l);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaf(l[i], LO_SCALE, v[i]);
+            }
             float4 o[2];
 #pragma unroll
             for (int qx = 0; qx < 2; ++qx) {
@@ -396,7 +443,13 @@ convt3d_s2_kernel(const ConvTParams p) {
 #pragma unroll
       for (int nb = 0; nb < NPAD / 32; ++nb) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NPAD + nb * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NACC + nb * 32), v);
+        if constexpr (X2) {
+          float l[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NACC + NPAD + nb * 32), l);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(l[i], LO_SCALE, v[i]);
+        }
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
           const int cgo = nb * 8 + g4;
@@ -419,30 +472,39 @@ convt3d_s2_kernel(const ConvTParams p) {
     tc_fence_before();
   } else if (lane == 0) {
     // ===================== MMA issuer (one thread) =============================================================
-    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, NPAD) : umma_idesc_tf32(128, NPAD);
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, NACC) : umma_idesc_tf32(128, NACC);
+    constexpr uint32_t idesc_lo = umma_idesc_f16(128, NPAD);   // X2: A_lo' x W_hi, the first NPAD columns of the same B tile
     bool first = true;
     int it = 0;
     for (int q = 0; q < n_q; ++q) {
-      int tz, kc, bz, by, bx;
-      if (!stage_of(q, tz, kc, bz, by, bx)) continue;
+      int tz, kc, ys, bz, by, bx;
+      if (!stage_of(q, tz, kc, ys, bz, by, bx)) continue;
       const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
       ++it;
       mbar_wait(&full[s], use & 1);
       tc_fence_after();
       const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
       const uint32_t sb = sa + Cfg::A_BYTES;
+      const int ty0 = ys * Cfg::ROWS;
 #pragma unroll
-      for (int ty = 0; ty < T; ++ty) {
+      for (int r = 0; r < Cfg::ROWS; ++r) {
+        const int ty = ty0 + r;
+        if (ty >= T) break;
 #pragma unroll
         for (int tx = 0; tx < T; ++tx) {
-          const uint64_t bdesc = umma_desc(sb + (ty * T + tx) * Cfg::B_TAP_BYTES, (NPAD / 8) * 128, 128);
+          const uint64_t bdesc = umma_desc(sb + (r * T + tx) * Cfg::B_TAP_BYTES, (NACC / 8) * 128, 128);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             // rows of this M-tile under tap (ty,tx): halo row (T-1-ty) + y, column (T-1-tx) + 8*mt + x
             const uint32_t a0 = sa + (((T - 1 - ty) * Cfg::PX) + (T - 1 - tx) + 8 * mt) * 16;
             const uint64_t adesc = umma_desc(a0, Cfg::A_CG_BYTES, Cfg::PX * 16);
-            if (F16) umma_f16(tmem_base + mt * NPAD, adesc, bdesc, idesc, !first || (ty | tx));
-            else umma_tf32(tmem_base + mt * NPAD, adesc, bdesc, idesc, !first || (ty | tx));
+            const bool acc = !first || (r | tx);
+            if (F16) umma_f16(tmem_base + mt * NACC, adesc, bdesc, idesc, acc);
+            else umma_tf32(tmem_base + mt * NACC, adesc, bdesc, idesc, acc);
+            if constexpr (X2) {
+              const uint64_t adesc_lo = umma_desc(a0 + CT_KCG * Cfg::A_CG_BYTES, Cfg::A_CG_BYTES, Cfg::PX * 16);
+              umma_f16(tmem_base + mt * NACC + NPAD, adesc_lo, bdesc, idesc_lo, true);
+            }
           }
         }
       }
@@ -458,10 +520,10 @@ convt3d_s2_kernel(const ConvTParams p) {
   }
 }
 
-template <int TZ, int T, int NPAD, int MT, int MODE, bool F16>
+template <int TZ, int T, int NPAD, int MT, int MODE, int OP>
 static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
-  using Cfg = ConvTCfg<T, NPAD, MT>;
-  auto kern = convt3d_s2_kernel<TZ, T, NPAD, MT, MODE, F16>;
+  using Cfg = ConvTCfg<T, NPAD, MT, OP == 2>;
+  auto kern = convt3d_s2_kernel<TZ, T, NPAD, MT, MODE, OP>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -481,23 +543,38 @@ static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
   return check_launch("convt3d_s2 kernel");
 }
 
-static thread_local bool g_conv_f16 = false;  // operand type of the next launch (set by the C ABI entry points)
+static thread_local int g_conv_op = 0;  // operand type of the next launch (set by the C ABI entry points): 0 TF32, 1 fp16, 2 fp16 hi/lo
+// X2 doubles the accumulator columns: halve the M-tiles per CTA until MT * 2 * NPAD fits the 512 TMEM columns
+template <int TZ, int T, int NPAD, int MT, int MODE>
+static int launch_convt_x2(const ConvTParams &p, cudaStream_t st) {
+  if constexpr (NPAD % 16 != 0 || 2 * NPAD > 256) {
+    return fail_arg(GENRE_B200_EINVAL, "convt3d: the fp16 hi/lo mode needs N = %d to be a multiple of 16, at most 128", NPAD);
+  } else if constexpr (MT * 2 * NPAD > 512) {
+    return launch_convt_x2<TZ, T, NPAD, MT / 2, MODE>(p, st);
+  } else {
+    return launch_convt_impl<TZ, T, NPAD, MT, MODE, 2>(p, st);
+  }
+}
+template <int TZ, int T, int NPAD, int MT, int MODE>
+static int launch_convt_op(const ConvTParams &p, cudaStream_t st) {
+  if (g_conv_op == 2) return launch_convt_x2<TZ, T, NPAD, MT, MODE>(p, st);
+  return g_conv_op == 1 ? launch_convt_impl<TZ, T, NPAD, MT, MODE, 1>(p, st) : launch_convt_impl<TZ, T, NPAD, MT, MODE, 0>(p, st);
+}
 template <int T, int NPAD, int MT, bool PAR>
 static int launch_convt(const ConvTParams &p, cudaStream_t st) {
-  return g_conv_f16 ? launch_convt_impl<T, T, NPAD, MT, PAR ? 0 : 1, true>(p, st)
-                    : launch_convt_impl<T, T, NPAD, MT, PAR ? 0 : 1, false>(p, st);
+  return launch_convt_op<T, T, NPAD, MT, PAR ? 0 : 1>(p, st);
 }
 template <int TZ, int T, int NPAD, int MT>
 static int launch_convt_merged(const ConvTParams &p, cudaStream_t st) {
-  return g_conv_f16 ? launch_convt_impl<TZ, T, NPAD, MT, 2, true>(p, st) : launch_convt_impl<TZ, T, NPAD, MT, 2, false>(p, st);
+  return launch_convt_op<TZ, T, NPAD, MT, 2>(p, st);
 }
 template <int MT>
 static int launch_convt_c1(const ConvTParams &p, cudaStream_t st) {
-  return g_conv_f16 ? launch_convt_impl<3, 3, 16, MT, 4, true>(p, st) : launch_convt_impl<3, 3, 16, MT, 4, false>(p, st);
+  return launch_convt_op<3, 3, 16, MT, 4>(p, st);
 }
 template <int T, int NPAD, int MT>
 static int launch_conv_merged8(const ConvTParams &p, cudaStream_t st) {
-  return g_conv_f16 ? launch_convt_impl<T, T, NPAD, MT, 3, true>(p, st) : launch_convt_impl<T, T, NPAD, MT, 3, false>(p, st);
+  return launch_convt_op<T, T, NPAD, MT, 3>(p, st);
 }
 
 }  // namespace gb
@@ -515,7 +592,7 @@ extern "C" int genre_b200_convt3d_s2_forward(const void *src0_, int cg0, const v
                                              int f16, const float *scale, const float *shift, float slope, float *out,
                                              int cgo, void *stream) {
   const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
-  g_conv_f16 = f16 != 0;
+  g_conv_op = f16;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "convt3d: null pointer");
   GB_REQUIRE(ksize == 4 || ksize == 8, GENRE_B200_EINVAL, "convt3d: kernel size %d unsupported (4 or 8)", ksize);
   GB_REQUIRE(npad == 32 || npad == 64, GENRE_B200_EINVAL, "convt3d: npad %d unsupported (32 or 64)", npad);
@@ -563,7 +640,7 @@ extern "C" int genre_b200_convt3d_s2_merged_forward(const void *src0_, int cg0, 
                                                     int npad, int f16, const float *scale, const float *shift,
                                                     float slope, float *out, int cgo, void *stream) {
   const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
-  g_conv_f16 = f16 != 0;
+  g_conv_op = f16;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "convt3d_merged: null pointer");
   GB_REQUIRE(ksize == 8, GENRE_B200_EINVAL, "convt3d_merged: kernel size %d unsupported (8)", ksize);
   GB_REQUIRE(npad == 80, GENRE_B200_EINVAL, "convt3d_merged: npad %d unsupported (80 = 4 classes x 20 channels)", npad);
@@ -601,7 +678,7 @@ extern "C" int genre_b200_conv3d_k8s2_s4d_forward(const void *src_, int cg, int6
                                                   const void *wpack_, int npad, int f16, const float *scale,
                                                   const float *shift, float slope, float *out, int cgo, void *stream) {
   const float *src = (const float *)src_, *wpack = (const float *)wpack_;
-  g_conv_f16 = f16 != 0;
+  g_conv_op = f16;
   GB_REQUIRE(src && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_k8s2_s4d: null pointer");
   GB_REQUIRE(npad == 160 || npad == 80, GENRE_B200_EINVAL,
              "conv3d_k8s2_s4d: npad %d unsupported (160 = 8 classes x 20 channels, or 80 = 4 (y,x) classes per z class)", npad);
@@ -632,7 +709,7 @@ extern "C" int genre_b200_convt_c1_tc_forward(const void *src0_, int cg0, const 
                                               int64_t H, int64_t W, const void *wpack_, int f16, const float *bias,
                                               int act_sigmoid, float *out, void *stream) {
   const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
-  g_conv_f16 = f16 != 0;
+  g_conv_op = f16;
   GB_REQUIRE(src0 && wpack && bias && out, GENRE_B200_EINVAL, "convt_c1_tc: null pointer");
   GB_REQUIRE(W == 16 || W == 32 || W == 64, GENRE_B200_EINVAL, "convt_c1_tc: input width %lld unsupported", (long long)W);
   GB_REQUIRE(H % CT_BY == 0 && H > 0 && D > 0 && B > 0, GENRE_B200_EINVAL, "convt_c1_tc: bad extent");
@@ -665,7 +742,7 @@ extern "C" int genre_b200_conv3d_taps_forward(const void *src0_, int cg0, const 
                                               int npad, int f16, const float *scale, const float *shift, float slope,
                                               float *out, int cgo, void *stream) {
   const float *src0 = (const float *)src0_, *src1 = (const float *)src1_, *wpack = (const float *)wpack_;
-  g_conv_f16 = f16 != 0;
+  g_conv_op = f16;
   GB_REQUIRE(src0 && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_taps: null pointer");
   GB_REQUIRE(taps == 3 || taps == 5, GENRE_B200_EINVAL, "conv3d_taps: %d taps unsupported (3 or 5)", taps);
   GB_REQUIRE(npad == 32 || (npad == 64 && taps == 3) || (npad == 96 && taps == 5), GENRE_B200_EINVAL,
@@ -719,7 +796,7 @@ extern "C" int genre_b200_conv3d_k4s2_forward(const void *src_, int cgs, int kbl
                                               int64_t W, const void *wpack_, int npad, int f16, const float *scale,
                                               const float *shift, float slope, float *out, int cgo, void *stream) {
   const float *src = (const float *)src_, *wpack = (const float *)wpack_;
-  g_conv_f16 = f16 != 0;
+  g_conv_op = f16;
   GB_REQUIRE(src && wpack && scale && shift && out, GENRE_B200_EINVAL, "conv3d_k4s2: null pointer");
   GB_REQUIRE(npad == 32 || npad == 64 || npad == 96 || npad == 128, GENRE_B200_EINVAL, "conv3d_k4s2: npad %d", npad);
   GB_REQUIRE(W == 16 || W == 32, GENRE_B200_EINVAL, "conv3d_k4s2: output width %lld unsupported (16 or 32)", (long long)W);

@@ -242,6 +242,44 @@ static unsigned ly_grid(size_t n) {
 
 using namespace gb;
 
+namespace gb {
+// fp32 blocked [BD][cg4][H][W][4] -> fp16 [BD][2][cg8][H][W][8]: part 0 = hi = fp16(a) (round to nearest), part 1 = lo' =
+// fp16((a - hi) * 2^11): a = hi + lo' * 2^-11 to ~2^-22 |a| (absolute floor ~1.5e-11).  The activation operand of the
+// fp32-accurate "f16x2" convolution mode (csrc/convt3d.cu X2).  |a| > 65504 becomes inf (and stays visible in the output).
+__global__ void __launch_bounds__(LY_THREADS)
+split2_f16_kernel(const float4 *__restrict__ src, uint4 *__restrict__ dst, int cg4, int cg8, size_t plane, size_t units) {
+  for (size_t u = (size_t)blockIdx.x * LY_THREADS + threadIdx.x; u < units; u += (size_t)gridDim.x * LY_THREADS) {
+    const size_t hw = u % plane;
+    size_t r = u / plane;
+    const int g = (int)(r % cg8);
+    r /= cg8;  // b * D + d
+    const float4 *s = src + (r * cg4 + 2 * g) * plane + hw;
+    const float4 a = __ldg(s);
+    const float4 b = 2 * g + 1 < cg4 ? __ldg(s + plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hi[i] = __float2half_rn(x[i]);
+      lo[i] = __float2half_rn((x[i] - __half2float(hi[i])) * 2048.0f);
+    }
+    uint4 ph, pl;
+    ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+    ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+    ph.z = (uint32_t)__half_as_ushort(hi[4]) | ((uint32_t)__half_as_ushort(hi[5]) << 16);
+    ph.w = (uint32_t)__half_as_ushort(hi[6]) | ((uint32_t)__half_as_ushort(hi[7]) << 16);
+    pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+    pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+    pl.z = (uint32_t)__half_as_ushort(lo[4]) | ((uint32_t)__half_as_ushort(lo[5]) << 16);
+    pl.w = (uint32_t)__half_as_ushort(lo[6]) | ((uint32_t)__half_as_ushort(lo[7]) << 16);
+    uint4 *o = dst + ((r * 2) * cg8 + g) * plane + hw;
+    o[0] = ph;
+    o[(size_t)cg8 * plane] = pl;
+  }
+}
+}  // namespace gb
+
+
 // mode 0: to_blocked, 1: s2d_blocked, 2: s2d_sources (cpad = padded channels per sub-volume; ignored otherwise),
 // 3: s4d_blocked.
 // group 4 -> fp32 units, 8 -> fp16 units.  src is contiguous NCDHW fp32.
@@ -337,4 +375,16 @@ extern "C" int genre_b200_blocked_split3(const float *src, int cg, int64_t BD, i
   const size_t plane = (size_t)(H * W), units = (size_t)BD * cg * plane;
   split3_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, (float4 *)dst, cg, plane, units);
   return check_launch("split3 kernel");
+}
+
+// blocked fp32 [BD][cg4][H][W][4] -> fp16 [BD][2][(cg4+1)/2][H][W][8] = (hi | lo' = (a - hi) * 2^11) parts: the activation
+// operand of the fp32-accurate "f16x2" convolution mode (2 MMAs per K step: A_hi x [W_hi | W_lo'] and A_lo' x W_hi)
+extern "C" int genre_b200_blocked_split2_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst,
+                                             void *stream) {
+  GB_REQUIRE(src && dst && cg4 > 0 && BD > 0 && H > 0 && W > 0, GENRE_B200_EINVAL, "blocked_split2_f16: bad argument");
+  GB_REQUIRE(aligned16(src) && aligned16(dst), GENRE_B200_EALIGN, "blocked_split2_f16: alignment");
+  const int cg8 = (cg4 + 1) / 2;
+  const size_t plane = (size_t)(H * W), units = (size_t)BD * cg8 * plane;
+  split2_f16_kernel<<<ly_grid(units), LY_THREADS, 0, as_stream(stream)>>>((const float4 *)src, (uint4 *)dst, cg4, cg8, plane, units);
+  return check_launch("split2_f16 kernel");
 }

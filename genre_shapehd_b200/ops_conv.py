@@ -102,10 +102,14 @@ class precision:
 
 
 def _mode():
-    """operand mode of the next launch: 'f16' | 'tf32' (single pass) or the fp32-accurate 'fp32x3' | 'f16x2'"""
+    """operand mode of the next launch: 'f16' | 'tf32' (single pass) or the fp32-accurate 'f16x2' | 'fp32x3'.
+    Inside _forced_mode("tf32") (gradient convolutions) an exact mode means fp32x3: gradients need fp32's exponent range,
+    which the fp16 hi/lo split does not have."""
     base = _OVERRIDE or PRECISION
     if base in _EXACT or not torch.backends.cudnn.allow_tf32:
-        return EXACT_IMPL if base not in ("fp32x3", "f16x2") else base
+        if _FORCED_MODE == "tf32" or base == "fp32x3":
+            return "fp32x3"
+        return base if base == "f16x2" else EXACT_IMPL
     return _FORCED_MODE or base
 
 
@@ -124,6 +128,15 @@ def _x3():
     return _mode() == "fp32x3"
 
 
+def _x2():
+    return _mode() == "f16x2"
+
+
+def _op_flag():
+    """`op` argument of the C ABI: 0 = TF32 operands, 1 = fp16, 2 = fp16 hi/lo split"""
+    return 2 if _x2() else 1 if _f16() else 0
+
+
 def _tf32_hi(w):
     """w rounded to TF32 (nearest, ties away - cvt.rna.tf32.f32) but kept in fp32 storage"""
     i = w.contiguous().view(torch.int32)
@@ -136,6 +149,30 @@ def _split3(t):
     out = torch.empty((bd, 3 * cg, h, w, 4), device=t.device, dtype=torch.float32)
     _lib.call("genre_b200_blocked_split3", t.data_ptr(), cg, bd, h, w, out.data_ptr(), _lib.stream_ptr(t))
     return out
+
+
+def _split2(t):
+    """blocked fp32 [BD,CG4,H,W,4] -> fp16 [BD, 2*CG8, H, W, 8]: CG8 = ceil(CG4/2) groups of hi = fp16(a) followed by CG8
+    groups of lo' = fp16((a - hi) * 2^11): the activation operand of the f16x2 mode (csrc/layout.cu split2_f16_kernel)"""
+    bd, cg4, h, w, _ = t.shape
+    cg8 = (cg4 + 1) // 2
+    out = torch.empty((bd, 2 * cg8, h, w, 8), device=t.device, dtype=torch.float16)
+    _lib.call("genre_b200_blocked_split2_f16", t.data_ptr(), cg4, bd, h, w, out.data_ptr(), _lib.stream_ptr(t))
+    return out
+
+
+def _finish_operand(xb):
+    """fp32 blocked conversion result -> the operand of the current exact mode (no-op for the single-pass modes)"""
+    if _x3():
+        return _split3(xb)
+    if _x2():
+        return _split2(xb)
+    return xb
+
+
+def _parts():
+    """operand parts stacked along the channel-group axis of an activation tensor (the kernels take per-part group counts)"""
+    return 2 if _x2() else 1
 
 
 def _x3_operands(src0, src1):
@@ -153,20 +190,29 @@ def _pack(module, key, make, chunk_dim, half=None):
     error scales with the partial sum it is added to)."""
     if half is None:
         half = _f16()
-    x3 = _x3()
+    x3, x2 = _x3(), _x2()
 
     def build(w):
         plan = _pack_plan(module, key, make)
+        if x2:      # [W_hi | W_lo'] side by side along N: the n-group axis is the third from last of every packed layout
+            hi = w.half().float()
+            return torch.cat((_apply_plan(plan, hi, True), _apply_plan(plan, (w - hi) * 2048.0, True)), dim=-3).contiguous()
         if not x3:
             return _apply_plan(plan, w, half)
         hi = _tf32_hi(w)
         p_hi, p_lo = _apply_plan(plan, hi, False), _apply_plan(plan, w - hi, False)
         return torch.cat((p_hi, p_lo, p_hi), dim=chunk_dim).contiguous()
-    return _cached_pack(module, key + (("x3",) if x3 else ("half",) if half else ()), build)
+    return _cached_pack(module, key + (("x2",) if x2 else ("x3",) if x3 else ("half",) if half else ()), build)
 
 
 def _group():
-    """channels per 16-byte channel group"""
+    """channels per 16-byte channel group of the kernel operands (weights, K-chunk sizing)"""
+    return 8 if (_f16() or _x2()) else 4
+
+
+def _act_group():
+    """channels per group of the NCDHW -> blocked conversions: fp16 groups of 8 in the single-pass fp16 mode; fp32 groups of 4
+    otherwise (the exact modes split them afterwards: _finish_operand)"""
     return 8 if _f16() else 4
 
 
@@ -195,6 +241,11 @@ def to_blocked(x, group=4, dtype=None):
 
 
 def _to_operand(x):
+    if _x2():   # the fp32 blocked twin a previous custom layer left behind saves the NCDHW round trip
+        twin = _cached_blocked(x)
+        if twin is not None and twin.shape[1] * 4 == x.shape[1] and twin.shape[0] == x.shape[0] * x.shape[2]:
+            return _split2(twin)
+        return _split2(to_blocked(x, 4))
     return to_blocked(x, 8, torch.float16) if _f16() else to_blocked(x, 4)
 
 
@@ -390,6 +441,7 @@ def convt3d_s2_blocked(src0, src1, batch, module, bn=None, slope=1.0):
     src0, src1 = _x3_operands(src0, src1)
     bd, cg0, h, w, _ = src0.shape
     cg1 = src1.shape[1] if src1 is not None else 0
+    cg0, cg1 = cg0 // _parts(), cg1 // _parts()
     cout = module.out_channels
     cgo = (cout + 3) // 4
     dev = src0.device
@@ -404,12 +456,12 @@ def convt3d_s2_blocked(src0, src1, batch, module, bn=None, slope=1.0):
         # the four (y,x) parity classes share one MMA stream: N = 4 x 20 columns (csrc/convt3d.cu MODE 2)
         wpack = _pack(module, ("convt_merged", 20, g), lambda wt: pack_convt_merged_weights(wt, 20, g), 2)
         _lib.call("genre_b200_convt3d_s2_merged_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None,
-                  cg1, batch, bd // batch, h, w, wpack.data_ptr(), 8, 80, 1 if g == 8 else 0, aff[0].data_ptr(),
+                  cg1, batch, bd // batch, h, w, wpack.data_ptr(), 8, 80, _op_flag() if g == 8 else 0, aff[0].data_ptr(),
                   aff[1].data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
         return out
     wpack = _pack(module, ("convt", npad, g), lambda wt: pack_convt_weights(wt, npad, g), 4)
     _lib.call("genre_b200_convt3d_s2_forward", src0.data_ptr(), cg0, src1.data_ptr() if src1 is not None else None, cg1,
-              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, 1 if g == 8 else 0,
+              batch, bd // batch, h, w, wpack.data_ptr(), module.kernel_size[0], npad, _op_flag() if g == 8 else 0,
               aff[0].data_ptr(), aff[1].data_ptr(), float(slope), out.data_ptr(), cgo, _lib.stream_ptr(src0))
     return out
 
@@ -527,15 +579,13 @@ def _conv_k4s2_s2d(x, m, bn, slope):
         return None
     cpad = -(-x.shape[1] * 8 // (2 * g)) * 2 * g          # the 8*Cin channels rounded up to whole K chunks
     wpack = _pack(m, ("k4s2_s2d", cpad, npad, g), lambda w: pack_conv_k4s2_s2d_weights(w, cpad, npad, g), 1)
-    xb = space_to_depth_blocked(x, g, torch.float16 if _f16() else None, cpad)
-    if _x3():
-        xb = _split3(xb)
+    xb = _finish_operand(space_to_depth_blocked(x, _act_group(), torch.float16 if _f16() else None, cpad))
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
     cgo = (cout + 3) // 4
     out = torch.empty((bd, cgo, h, w, 4), device=x.device, dtype=torch.float32)
-    _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg, None, 0, b, bd // b, h, w, wpack.data_ptr(), 3, 1, npad,
-              1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
+    _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg // _parts(), None, 0, b, bd // b, h, w, wpack.data_ptr(), 3, 1, npad,
+              _op_flag(), aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
               out.data_ptr(), cgo, _lib.stream_ptr(x))
     return from_blocked(out, b, cout)
 
@@ -664,15 +714,13 @@ def _conv_k4s2(x, m, bn, slope):
     cin = x.shape[1]
     cpad = (cin + 2 * g - 1) // (2 * g) * (2 * g)      # a K chunk (2 channel groups) must not straddle sub-volumes
     wpack = _pack(m, ("k4s2", cpad, npad, g), lambda w: pack_conv_k4s2_weights(w, cpad, npad, g), 1)
-    xb = space_to_depth_sources(x, cpad, g, torch.float16 if _f16() else None)
-    if _x3():
-        xb = _split3(xb)
+    xb = _finish_operand(space_to_depth_sources(x, cpad, _act_group(), torch.float16 if _f16() else None))
     b = x.shape[0]
     bd, _, h, wd, _ = xb.shape
     cgo = (cout + 3) // 4
     out = torch.empty((bd, cgo, h, wd, 4), device=x.device, dtype=torch.float32)
     _lib.call("genre_b200_conv3d_k4s2_forward", xb.data_ptr(), cpad // g, 3 if _x3() else 1, b, bd // b, h, wd, wpack.data_ptr(), npad,
-              1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
+              _op_flag(), aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
               out.data_ptr(), cgo, _lib.stream_ptr(x))
     return from_blocked(out, b, cout)
 
@@ -914,16 +962,15 @@ def conv3d(x, m, bn=None, slope=None):
         if aff is None:
             return None
         g, b, cout = _group(), x.shape[0], m.out_channels
-        wpack = _pack(m, ("k8s2_s4d", 20, g, S4D_SPLIT_Z), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g, S4D_SPLIT_Z),
-                      2 if S4D_SPLIT_Z else 1)
-        xb = space_to_depth4_blocked(x, g, torch.float16 if _f16() else None)
-        if _x3():
-            xb = _split3(xb)
+        split_z = S4D_SPLIT_Z or _x2()     # f16x2 doubles the accumulator columns: 8 classes x 20 x 2 = 320 > 256, 4 classes fit
+        wpack = _pack(m, ("k8s2_s4d", 20, g, split_z), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g, split_z),
+                      2 if split_z else 1)
+        xb = _finish_operand(space_to_depth4_blocked(x, _act_group(), torch.float16 if _f16() else None))
         bd, cg, h, w, _ = xb.shape
         cgo = (cout + 3) // 4
         out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=x.device, dtype=torch.float32)
-        _lib.call("genre_b200_conv3d_k8s2_s4d_forward", xb.data_ptr(), cg, b, bd // b, h, w, wpack.data_ptr(), 80 if S4D_SPLIT_Z else 160,
-                  1 if _f16() else 0, aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
+        _lib.call("genre_b200_conv3d_k8s2_s4d_forward", xb.data_ptr(), cg // _parts(), b, bd // b, h, w, wpack.data_ptr(), 80 if split_z else 160,
+                  _op_flag(), aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope),
                   out.data_ptr(), cgo, _lib.stream_ptr(x))
         return from_blocked(out, b, cout)
     cout, npad = m.out_channels, 32
@@ -932,15 +979,13 @@ def conv3d(x, m, bn=None, slope=None):
         return None
     sc, sh = aff
     dev = x.device
-    xb = space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x)
-    if _x3():
-        xb = _split3(xb)
+    xb = _finish_operand(space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x))
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
     cgo = (cout + 3) // 4
     out = torch.empty((bd, cgo, h, w, 4), device=dev, dtype=torch.float32)
-    _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg, None, 0, b, bd // b, h, w,
-              _packed_conv(m, npad).data_ptr(), 5, 2, npad, 1 if _f16() else 0, sc.data_ptr(), sh.data_ptr(),
+    _lib.call("genre_b200_conv3d_taps_forward", xb.data_ptr(), cg // _parts(), None, 0, b, bd // b, h, w,
+              _packed_conv(m, npad).data_ptr(), 5, 2, npad, _op_flag(), sc.data_ptr(), sh.data_ptr(),
               1.0 if slope is None else float(slope), out.data_ptr(), cgo, _lib.stream_ptr(x))
     return from_blocked(out, b, cout)
 
@@ -966,8 +1011,8 @@ def convt_c1_tc(inputs, m, sigmoid=False):
     """ConvTranspose3d(Cin -> 1, k4, s2, p1) over the channel concatenation of `inputs` on the tensor cores (MODE 4);
     NCDHW [B,1,2D,2H,2W] or None if not covered."""
     x0 = inputs[0]
-    if _x3():
-        return None   # fp32 wanted: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and cheaper than 3x the TF32 MMAs
+    if _x3() or _x2():
+        return None   # fp32 wanted: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and cheaper than the split-operand MMAs
     if not ("convt_c1_tc" in POLICY and ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
             and tuple(m.padding) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1)
             and m.groups == 1 and m.out_channels == 1 and len(inputs) <= 2

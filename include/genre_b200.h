@@ -339,6 +339,13 @@ int genre_b200_scale_clamp_strided(const float *src, int64_t maps, int64_t n, fl
  * fp32 output of one tensor-core layer into the fp16 operand of the next without going through NCDHW */
 int genre_b200_blocked_f32_to_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst, void *stream);
 
+/* blocked fp32 [BD][cg4][H][W][4] -> fp16 [BD][2 parts][(cg4+1)/2][H][W][8]: part 0 = hi = fp16(a), part 1 = lo' =
+ * fp16((a - hi) * 2^11).  The activation operand of the conv kernels' op = 2 ("f16x2") mode: the fp32-accurate replacement of
+ * the reference's fp32 cuDNN convolutions (networks/networks.py:197-218) at 2 tensor-core MMAs per K step
+ * (A_hi x [W_hi | W_lo'] and A_lo' x W_hi; weights packed [W_hi | W_lo'] along N by ops_conv._pack).  In that mode every
+ * conv entry point above takes per-part channel-group counts and `f16` = 2. */
+int genre_b200_blocked_split2_f16(const float *src, int cg4, int64_t BD, int64_t H, int64_t W, void *dst, void *stream);
+
 /* blocked fp32 [BD][cg][H][W][4] -> [BD][3*cg][H][W][4] = (lo | hi | hi): hi = value rounded to TF32, lo = value - hi.
  * With weights packed as (W_hi | W_lo | W_hi) along K, the TF32 tensor-core kernels above compute
  * A_lo*W_hi + A_hi*W_lo + A_hi*W_hi = the fp32 product to ~2^-21 relative (small terms first: the tensor core's

@@ -347,3 +347,27 @@ def test_weight_gradient_formulas_of_the_fp32_pipe_kernels():
                 xs = xp[:, :, kz:kz + 2 * do:2, ky:ky + 2 * ho:2, kx:kx + 2 * wo:2]    # x[b, ci, 2o - 3 + k]
                 dw[:, :, kz, ky, kx] = torch.einsum("bozyx,bizyx->oi", gy, xs)
     assert torch.allclose(dw, rw, atol=1e-9)
+
+
+def test_f16x2_weight_packing_is_hi_and_scaled_lo_side_by_side():
+    """ops_conv._pack in the f16x2 mode: [W_hi | W_lo'] along the n-group axis of the packed layout, W_hi = fp16(w),
+    W_lo' = fp16((w - W_hi) * 2^11); W_hi + W_lo' / 2^11 reproduces the weights to ~2^-22"""
+    import torch.nn as nn
+    torch.manual_seed(31)
+    m = nn.ConvTranspose3d(16, 5, 8, 2, 3)
+    with ops_conv.precision("f16x2"):
+        assert ops_conv._x2() and ops_conv._group() == 8 and ops_conv._act_group() == 4 and ops_conv._op_flag() == 2 and ops_conv._parts() == 2
+        packed = ops_conv._pack(m, ("convt_merged", 8, 8), lambda wt: ops_conv.pack_convt_merged_weights(wt, 8, 8), 2)
+    w = m.weight.detach()
+    hi = w.half().float()
+    p_hi = ops_conv.pack_convt_merged_weights(hi, 8, 8)
+    p_lo = ops_conv.pack_convt_merged_weights((w - hi) * 2048.0, 8, 8)
+    assert packed.dtype == torch.float16 and packed.shape[-3] == 2 * p_hi.shape[-3]
+    n = p_hi.shape[-3]
+    assert torch.equal(packed[..., :n, :, :], p_hi) and torch.equal(packed[..., n:, :, :], p_lo)
+    rec = packed[..., :n, :, :].float() + packed[..., n:, :, :].float() / 2048.0
+    with ops_conv.precision("tf32"):
+        plain = ops_conv._apply_plan(ops_conv._pack_plan(m, ("convt_merged", 8, 8), lambda wt: ops_conv.pack_convt_merged_weights(wt, 8, 8)), w, False)
+    assert ((rec - plain).abs() <= 2.0 ** -21 * plain.abs() + 2e-11).all()
+    with ops_conv.precision("f16x2"), ops_conv._forced_mode("tf32"):      # gradient convolutions keep fp32's exponent range
+        assert ops_conv._mode() == "fp32x3"

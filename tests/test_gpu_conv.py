@@ -30,12 +30,16 @@ def _tol():
     1e-4 for the 3xTF32 mode (north_star: values within 1e-4).  Measured for 3xTF32: 1e-6 .. 4e-5, growing with the number
     of MMA steps per output (3000 for Unet_3D.dec5) because the tensor core's fp32 accumulator truncates (~2^-25 of the
     partial sum per step); the operand split itself is good to 2^-21."""
-    return 1e-4 if ops_conv.PRECISION == "fp32x3" else 4e-3
+    return 1e-4 if ops_conv.PRECISION in EXACT_MODES else 4e-3
 
 
-@pytest.fixture(autouse=True, params=["f16", "tf32", "fp32x3"])
+EXACT_MODES = ("fp32x3", "f16x2")
+
+
+@pytest.fixture(autouse=True, params=["f16", "tf32", "fp32x3", "f16x2"])
 def _precision(request):
-    """every test runs with the three operand modes of the tensor-core kernels"""
+    """every test runs with the four operand modes of the tensor-core kernels: two single-pass ones (10-bit mantissa) and
+    the two fp32-accurate operand splits (3xTF32 along K; fp16 hi/lo with separate accumulators)"""
     torch.backends.cudnn.allow_tf32 = True   # the custom kernels decline when reduced-mantissa convolutions are disallowed
     old, oldp = ops_conv.PRECISION, set(ops_conv.POLICY)
     ops_conv.PRECISION = request.param
@@ -233,7 +237,7 @@ def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
 def test_convt_c1_tensor_core_vs_torch(chans, b, d, h, w, sigmoid):
     """MODE 4: ConvT(Cin -> 1) as 27 union taps x 8 output classes on the tensor cores; one or two (skip) sources, the
     20-channel ones arriving as blocked twins of a previous custom layer (zero-padded to the operand group size)"""
-    if ops_conv.PRECISION == "fp32x3":
+    if ops_conv.PRECISION in EXACT_MODES:
         pytest.skip("fp32 wanted: the 1-channel layer goes to the exact FP32-pipe kernel instead (test_dec6_two_source_path)")
     torch.manual_seed(sum(chans) + w)
     m = nets.ConvTranspose3d(sum(chans), 1, 4, 2, 1).to(DEV)
@@ -318,7 +322,7 @@ def test_fused_sequential_matches_module_by_module(name):
         y = net(x)
         with fp32_reference():
             ref = net(x)
-    tol = 2e-4 if ops_conv.PRECISION == "fp32x3" else 2e-2
+    tol = 2e-4 if ops_conv.PRECISION in EXACT_MODES else 2e-2
     # the critic has no normalisation layers and its scalar output is a heavily cancelling sum: floor the scale
     assert (y - ref).abs().max().item() <= tol * max(1e-2, ref.abs().max().item())
 
@@ -502,3 +506,36 @@ def test_bn_act_train_forward_backward_vs_torch(shape, act):
     assert (bn.bias.grad - ref_bn.bias.grad).abs().max().item() <= 1e-3 * max(1.0, ref_bn.bias.grad.abs().max().item())
     assert torch.allclose(bn.running_mean, ref_bn.running_mean, atol=1e-5) and torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-4)
     assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+
+
+def test_split2_f16_layout_kernel_is_the_hi_lo_decomposition():
+    """csrc/layout.cu split2_f16_kernel against its definition in torch: hi = fp16(a), lo' = fp16((a - hi) * 2^11), parts stacked
+    along the channel-group axis, odd group counts zero-padded; hi + lo' / 2^11 reproduces a to ~2^-22"""
+    torch.manual_seed(3)
+    t = torch.randn(6, 5, 16, 16, 4, device=DEV) * torch.logspace(-6, 2, 5, device=DEV).view(1, 5, 1, 1, 1)
+    out = ops_conv._split2(t)
+    assert out.shape == (6, 6, 16, 16, 8) and out.dtype == torch.float16
+    pad = torch.cat((t, torch.zeros_like(t[:, :1])), dim=1)                           # 6 groups of 4 -> 3 groups of 8
+    x8 = torch.cat((pad[:, 0::2], pad[:, 1::2]), dim=-1)
+    hi = x8.half()
+    lo = ((x8 - hi.float()) * 2048.0).half()
+    assert torch.equal(out[:, :3], hi) and torch.equal(out[:, 3:], lo)
+    rec = out[:, :3].float() + out[:, 3:].float() / 2048.0
+    assert ((rec - x8).abs() <= 2.0 ** -21 * x8.abs() + 2e-11).all()
+
+
+def test_f16x2_matches_fp32_much_closer_than_single_pass():
+    """the point of the mode: the dominant refiner layer (ConvT 80 -> 20, k8: 1000 K steps per output) within 2e-5 of fp32
+    where single-pass fp16 operands sit at ~1e-3"""
+    torch.manual_seed(21)
+    m = nets.ConvTranspose3d(80, 20, 8, 2, 3).to(DEV)
+    x = torch.randn(2, 80, 4, 32, 32, device=DEV)
+    with torch.no_grad():
+        ref = _ref(x, m)
+        errs = {}
+        for mode in ("f16", "f16x2", "fp32x3"):
+            with ops_conv.precision(mode):
+                y = ops_conv.conv_transpose3d(x, m)
+            assert y is not None
+            errs[mode] = ((y - ref).abs().max() / ref.abs().max()).item()
+    assert errs["f16x2"] <= 2e-5 and errs["f16x2"] < errs["f16"] / 20, errs
