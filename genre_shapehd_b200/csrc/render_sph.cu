@@ -158,19 +158,28 @@ render_spherical_forward_kernel(const float *__restrict__ vox, int R, const doub
 
 // ---- empty-space skipping (forward) ---------------------------------------------------------------------------------
 // GenRe renders a thin shell: clamp(proj * 50, 1e-5, 1 - 1e-5) is 1e-5 everywhere except on the ~1 % of voxels the depth
-// map hit, and a third of every ray lies outside the volume, yet the plain kernel pays 8 gathers + fp64 positions for each
-// of its 4.19 M samples per shape.  A sample whose 8 taps are all <= 1e-5 (or outside: zero padding) clamps to p = 1e-5
-// (up to a 1e-12 rounding of the interpolation): a run of such samples has a closed form.
-//   pre-pass  (render_occupancy_kernel): one read of the volume -> a bit per 8^3 brick, set when any voxel within the brick
-//             DILATED by one voxel exceeds 1e-5 (the dilation covers the +1 taps and the fp32 position estimate below);
-//   render    per 32-sample chunk each lane locates its sample's brick from an fp32 estimate of the position (3 FMAs);
-//             if the whole chunk is empty (warp vote):  acc += 1e-5 * T * CW[c],  T *= Q[c]
-//             with CW[c] = sum_j q^j w_{32c+j}, Q[c] = q^(samples in chunk), q = 1 - 1e-5 (tables built per CTA);
-//             otherwise the chunk takes the exact path (fp64 positions, 8 taps), lanes on empty samples skipping their gathers.
-// Error of the closed form against the sample-by-sample product: a few 1e-7 relative on T (bounded by 1e-6 over a ray).
+// map hit, and a third of every ray lies outside the volume, yet the plain kernel pays ~200 instructions (fp64 position,
+// 8 gathers, scan) for each of its 4.19 M samples per shape: it is issue-bound (ncu: 412 M warp instructions, 78 % issue
+// active, profiles/r02_render_summary.md).  A sample whose 8 taps are all <= 1e-5 (or outside: zero padding) clamps to
+// p = 1e-5 (up to a 1e-12 rounding of the interpolation), and a run of such samples has a closed form:
+//     T after n samples = T * q^n,     sum_k s_k w_k over the run = 1e-5 * T * (S[b] - S[a]) / q^a,
+//     q = 1 - 1e-5,   S[k] = sum_{j<k} q^j w_j  (prefix table built per CTA from the caller's depth_weight buffer).
+//   pre-pass  (render_occupancy_*): one read of the volume -> a bit per 8^3 brick b, set when any voxel in [8b-1, 8b+9]
+//             per dimension exceeds 1e-5: a sample at voxel coordinate f reads taps floor(f), floor(f)+1, so the brick
+//             floor(f/8) covers both (+8), the -1 / +9 absorb the fp32 estimate of f used for the lookup;
+//   render    a warp owns 4 neighbouring rays x 8 consecutive samples per step.  The bounding box of the marked bricks
+//             gives each ray a sample range [K0, K1): everything before and after it is ONE closed-form update.  Inside,
+//             every lane looks its sample's brick up in a 32^3-brick padded bitmask in shared memory (3 FMAs + 3 floors:
+//             positions anywhere in [-2, 2]^3 index it without range checks); a step whose 32 samples are all empty is a
+//             closed-form update, otherwise the lanes on occupied bricks take the exact path (fp64 positions, 8 taps) and the
+//             transmittance is scanned inside each 8-lane group.
+// Error against the sample-by-sample product: a few 1e-7 relative on T (measured <= 4e-6 on the output).
 constexpr int RS_BRICK = 8;
-constexpr int RS_RAYS_PER_WARP = 4;
-constexpr int RS_MAX_Z_CHUNKS = 32;  // Z <= 1024 on the skipping path
+constexpr int RS_NB_MAX = 16;         // bricks per dimension the padded mask covers (res <= 128)
+constexpr int RS_PAD = 8;             // padding bricks on each side: |coord| <= 2  ->  brick index in [-8, 24)
+constexpr int RS_PB = 32;             // padded bricks per dimension
+constexpr int RS_GROUPS_PER_WARP = 4; // 4-ray groups a warp walks one after the other (16 rays per warp, 128 per CTA)
+constexpr int RS_MAX_Z = 1024;
 constexpr float RS_LOG2_Q = -1.4427022e-05f;  // log2(1 - 1e-5)
 
 __host__ __device__ inline int rs_bricks(int R) { return (R + RS_BRICK - 1) / RS_BRICK; }
@@ -179,11 +188,11 @@ __host__ __device__ inline int rs_occ_words(int R) {
   return (nb * nb * nb + 31) / 32;
 }
 
+// generic pre-pass: one thread per 4 z-adjacent voxels (R % 4 == 0); blockIdx.y = volume
 template <bool PRE>
 __global__ void __launch_bounds__(256)
 render_occupancy_kernel(const float *__restrict__ vox, int R, long long vox_per_vol4, unsigned *__restrict__ occ,
                         const VoxPre pre) {
-  // one thread per 4 z-adjacent voxels (R % 4 == 0); blockIdx.y = volume
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= vox_per_vol4) return;
   const int n = blockIdx.y;
@@ -202,9 +211,10 @@ render_occupancy_kernel(const float *__restrict__ vox, int R, long long vox_per_
   const long long lin = i4 * 4;
   const int z = (int)(lin % R), y = (int)((lin / R) % R), x = (int)(lin / ((long long)R * R));
   const int nb = rs_bricks(R);
-  const int bx0 = max(x - 1, 0) / RS_BRICK, bx1 = min(x + 1, R - 1) / RS_BRICK;
-  const int by0 = max(y - 1, 0) / RS_BRICK, by1 = min(y + 1, R - 1) / RS_BRICK;
-  const int bz0 = max(z + zlo - 1, 0) / RS_BRICK, bz1 = min(z + zhi + 1, R - 1) / RS_BRICK;
+  // brick b is marked iff an occupied voxel lies in [8b - 1, 8b + 9]  <=>  b in [floor((v - 2) / 8), floor((v + 1) / 8)]
+  const int bx0 = max(x - 2, 0) / RS_BRICK, bx1 = min(x + 1, R - 1) / RS_BRICK;
+  const int by0 = max(y - 2, 0) / RS_BRICK, by1 = min(y + 1, R - 1) / RS_BRICK;
+  const int bz0 = max(z + zlo - 2, 0) / RS_BRICK, bz1 = min(z + zhi + 1, R - 1) / RS_BRICK;
   unsigned *o = occ + (size_t)n * rs_occ_words(R);
   for (int bx = bx0; bx <= bx1; ++bx)
     for (int by = by0; by <= by1; ++by)
@@ -215,78 +225,204 @@ render_occupancy_kernel(const float *__restrict__ vox, int R, long long vox_per_
       }
 }
 
+// R = 128 pre-pass: a warp owns whole z rows (32 lanes x 4 voxels = 128), 4 rows in flight per iteration; a row's 16 z-brick
+// bits are OR-reduced across the warp and merged into the (at most 2 x 2) brick columns its dilated (x, y) touches.
+template <bool PRE>
+__global__ void __launch_bounds__(256)
+render_occupancy128_kernel(const float *__restrict__ vox, unsigned *__restrict__ occ, const VoxPre pre) {
+  constexpr int R = 128, ROWS = 4;
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row0 = warp_global * ROWS;  // row index = x * R + y
+  if (row0 >= R * R) return;
+  const float4 *base = reinterpret_cast<const float4 *>(vox + (size_t)n * R * R * R) + (size_t)row0 * 32 + lane;
+  float4 v[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) v[r] = __ldcs(base + r * 32);
+  unsigned *o = occ + (size_t)n * rs_occ_words(R);
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const float a[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+    unsigned zmask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float t = PRE ? fminf(fmaxf(__fmul_rn(a[i], pre.scale), pre.lo), pre.hi) : a[i];
+      if (!(t <= RS_PMIN)) {
+        const int z = lane * 4 + i;
+        zmask |= (1u << (max(z - 2, 0) >> 3)) | (1u << (min(z + 1, R - 1) >> 3));
+      }
+    }
+    zmask = __reduce_or_sync(0xffffffffu, zmask);
+    if (zmask == 0 || lane >= 4) continue;
+    const int row = row0 + r, x = row >> 7, y = row & 127;
+    const int bx = (lane & 1) ? min(x + 1, R - 1) >> 3 : max(x - 2, 0) >> 3;
+    const int by = (lane & 2) ? min(y + 1, R - 1) >> 3 : max(y - 2, 0) >> 3;
+    // bit = (bx*16 + by)*16 + bz: word = bx*8 + (by >> 1), the row's 16 bits at (by & 1) * 16
+    unsigned *w = o + bx * 8 + (by >> 1);
+    const unsigned m = zmask << ((by & 1) * 16);
+    if ((*w & m) != m) atomicOr(w, m);
+  }
+}
+
 template <bool PRE>
 __global__ void __launch_bounds__(RS_THREADS)
 render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const double *__restrict__ dirs, int S, int Z,
                                      const float *__restrict__ depth_weight, const unsigned *__restrict__ occ,
                                      float *__restrict__ out, const VoxPre pre) {
-  extern __shared__ unsigned rs_smem[];
-  const int words = rs_occ_words(R), nchunk = (Z + 31) / 32;
-  unsigned *s_occ = rs_smem;
-  float *s_cw = reinterpret_cast<float *>(rs_smem + words);  // [nchunk]
-  float *s_qn = s_cw + RS_MAX_Z_CHUNKS;                       // [nchunk]
-  const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < words; i += RS_THREADS) s_occ[i] = occ[(size_t)n * words + i];
-  const float qpow = exp2f((float)lane * RS_LOG2_Q);
-  for (int c = warp; c < nchunk; c += RS_THREADS / 32) {
-    const int k = c * 32 + lane;
-    const float cw = warp_sum(k < Z ? qpow * __ldg(depth_weight + k) : 0.0f);
-    if (lane == 0) {
-      s_cw[c] = cw;
-      s_qn[c] = exp2f((float)min(32, Z - c * 32) * RS_LOG2_Q);
+  __shared__ unsigned s_occ[RS_PB * RS_PB];  // padded brick mask: word = X * 32 + Y, bit = Z (padded brick coordinates)
+  __shared__ float s_S[RS_MAX_Z + 1];        // S[k] = sum_{j<k} q^j w_j
+  __shared__ float s_cw8[RS_MAX_Z / 8];      // sum_{j<8} q^j w_{8s+j}
+  __shared__ int s_box[6];                   // marked-brick bounding box: min x,y,z, max x,y,z (unpadded brick coordinates)
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = rs_bricks(R), words = rs_occ_words(R);
+  for (int i = tid; i < RS_PB * RS_PB; i += RS_THREADS) s_occ[i] = 0;
+  if (tid < 3) s_box[tid] = nb;
+  else if (tid < 6) s_box[tid] = -1;
+  // prefix table of q^j w_j: warp 0, 32 entries per pass
+  if (warp == 0) {
+    float run = 0.0f;
+    for (int k0 = 0; k0 < Z; k0 += 32) {
+      const int k = k0 + lane;
+      float v = k < Z ? exp2f((float)k * RS_LOG2_Q) * __ldg(depth_weight + k) : 0.0f;
+      float incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
+      }
+      if (k < Z) s_S[k + 1] = run + incl;
+      run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) s_S[0] = 0.0f;
   }
   __syncthreads();
-  const int nb = rs_bricks(R);
+  // expand the compact mask into the padded one and take its bounding box
+  for (int wi = tid; wi < words; wi += RS_THREADS) {
+    const unsigned wv = occ[(size_t)n * words + wi];
+    if (!wv) continue;
+    for (unsigned rem = wv; rem;) {
+      const int b = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const int bit = wi * 32 + b;
+      const int bz = bit % nb, by = (bit / nb) % nb, bx = bit / (nb * nb);
+      // f in (-1, 0) reads voxel 0 but floors to brick -1: a marked boundary brick also marks its outside neighbour(s)
+      const unsigned zb = (1u << (bz + RS_PAD)) | (bz == 0 ? 1u << (RS_PAD - 1) : 0u);
+      for (int ex = (bx == 0 ? -1 : 0); ex <= 0; ++ex)
+        for (int ey = (by == 0 ? -1 : 0); ey <= 0; ++ey) atomicOr(&s_occ[(bx + ex + RS_PAD) * RS_PB + (by + ey + RS_PAD)], zb);
+      atomicMin(&s_box[0], bx); atomicMin(&s_box[1], by); atomicMin(&s_box[2], bz);
+      atomicMax(&s_box[3], bx); atomicMax(&s_box[4], by); atomicMax(&s_box[5], bz);
+    }
+  }
+  for (int s8 = tid; s8 * 8 < Z; s8 += RS_THREADS) {
+    const int a = s8 * 8, b = min(a + 8, Z);
+    s_cw8[s8] = (s_S[b] - s_S[a]) * exp2f(-(float)a * RS_LOG2_Q);
+  }
+  __syncthreads();
+  const bool any = s_box[3] >= 0;
+  // sample-space box: a sample looks up brick floor(f / 8) (f in [-8, 0) finds the copies of boundary marks)
+  float blo[3], bhi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    blo[d] = s_box[d] == 0 ? -8.01f : 8.0f * s_box[d] - 0.01f;
+    bhi[d] = 8.0f * (s_box[3 + d] + 1) + 0.01f;
+  }
   const float h = 0.5f * (float)(R - 1), stepf = Z > 1 ? 1.0f / (float)(Z - 1) : 0.0f;
   const double step = Z > 1 ? 1.0 / (double)(Z - 1) : 0.0;
   const float *vol = vox + (size_t)n * R * R * R;
-  const int pix0 = (blockIdx.x * (RS_THREADS / 32) + warp) * RS_RAYS_PER_WARP;
-  for (int rr = 0; rr < RS_RAYS_PER_WARP; ++rr) {
-    const int pix = pix0 + rr;
-    if (pix >= S * S) break;  // warp-uniform
-    const double dx = dirs[pix * 3 + 0], dy = dirs[pix * 3 + 1], dz = dirs[pix * 3 + 2];
+  const int j = lane & 7, grp = lane >> 3;
+  const int nsteps = (Z + 7) / 8;
+  const float q8 = exp2f(8.0f * RS_LOG2_Q);
+  for (int gi = 0; gi < RS_GROUPS_PER_WARP; ++gi) {
+    const int pix_base = ((blockIdx.x * (RS_THREADS / 32) + warp) * RS_GROUPS_PER_WARP + gi) * 4;
+    if (pix_base >= S * S) break;  // warp-uniform
+    const int pix = pix_base + grp;
+    const bool ray_ok = pix < S * S;
+    const int pixc = ray_ok ? pix : S * S - 1;
+    const double dx = dirs[pixc * 3 + 0], dy = dirs[pixc * 3 + 1], dz = dirs[pixc * 3 + 2];
     const double dx2 = dx * 2.0, dy2 = dy * 2.0, dz2 = dz * 2.0;
-    const float dxh = (float)dx * h, dyh = (float)dy * h, dzh = (float)dz * h;
-    float carry = 1.0f, acc = 0.0f, acc_u = 0.0f;
-    for (int c = 0; c < nchunk; ++c) {
-      const int k = c * 32 + lane;
-      bool empty = true;
-      if (k < Z) {
-        const float r = 2.0f * (1.0f - (float)k * stepf);  // |position| in normalised units (0 at the centre)
-        const float fx = fmaf(dxh, r, h), fy = fmaf(dyh, r, h), fz = fmaf(dzh, r, h);
-        const float lo = -1.01f, hi = (float)R + 0.01f;      // taps floor(f), floor(f)+1: all invalid outside (-1, R)
-        if (fx > lo && fx < hi && fy > lo && fy < hi && fz > lo && fz < hi) {
-          const int bx = min(max((int)floorf(fx), 0), R - 1) / RS_BRICK, by = min(max((int)floorf(fy), 0), R - 1) / RS_BRICK,
-                    bz = min(max((int)floorf(fz), 0), R - 1) / RS_BRICK;
-          const int bit = (bx * nb + by) * nb + bz;
-          empty = !((s_occ[bit >> 5] >> (bit & 31)) & 1u);
-        }
+    // voxel coordinate of sample k (fp32 estimate): f = h + d*h*2*(1 - k*step) = A - Bk * k
+    const float A[3] = {h + 2.0f * (float)dx * h, h + 2.0f * (float)dy * h, h + 2.0f * (float)dz * h};
+    const float Bk[3] = {2.0f * (float)dx * h * stepf, 2.0f * (float)dy * h * stepf, 2.0f * (float)dz * h * stepf};
+    // this ray's sample range inside the box (slab test on the real-valued sample index)
+    float kmin = 0.0f, kmax = (float)Z;
+    if (!any || !ray_ok) kmax = -1.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (fabsf(Bk[d]) > 1e-12f) {
+        const float inv = 1.0f / Bk[d];
+        const float k1 = (A[d] - blo[d]) * inv, k2 = (A[d] - bhi[d]) * inv;
+        kmin = fmaxf(kmin, fminf(k1, k2));
+        kmax = fminf(kmax, fmaxf(k1, k2));
+      } else if (A[d] < blo[d] || A[d] > bhi[d]) {
+        kmax = -1.0f;
       }
-      if (__all_sync(0xffffffffu, empty)) {
-        acc_u = fmaf(RS_PMIN * carry, s_cw[c], acc_u);
-        carry *= s_qn[c];
-        continue;
-      }
-      float p = 0.0f;  // lanes past the end behave like p = 0 (factor 1, no contribution)
-      if (k < Z) {
-        p = RS_PMIN;
-        if (!empty) {
-          float gx, gy, gz;
-          ray_point(dx2, dy2, dz2, k, Z, step, gx, gy, gz);
-          Taps t;
-          make_taps(gx, gy, gz, R, t);
-          p = fminf(fmaxf(sample_trilinear<PRE>(vol, t, R, pre), RS_PMIN), RS_PMAX);
-        }
-      }
-      float total;
-      const float before = carry * warp_excl_prod32(1.0f - p, total);
-      if (k < Z) acc = fmaf(p * before, __ldg(depth_weight + k), acc);
-      carry *= total;
-      if (carry == 0.0f) break;  // transmittance underflowed: every later term is exactly 0 (warp-uniform)
     }
-    const float e = warp_sum(acc) + acc_u;
-    if (lane == 0) out[(size_t)n * S * S + pix] = e + carry;
+    int s0 = nsteps, s1 = 0;  // steps [s0, s1) need per-sample tests
+    if (kmax >= kmin) {
+      s0 = max(0, (int)floorf(kmin) - 1) >> 3;
+      s1 = min(nsteps, (min(Z, (int)ceilf(kmax) + 2) + 7) >> 3);
+      if (s1 <= s0) { s0 = nsteps; s1 = 0; }
+    }
+    s0 = __reduce_min_sync(0xffffffffu, s0);
+    s1 = __reduce_max_sync(0xffffffffu, s1);
+    float T = 1.0f, acc = 0.0f, acc_u = 0.0f;
+    int kdone = 0;  // samples [0, kdone) are accounted for
+    if (s0 < s1) {
+      // head: samples [0, 8*s0) in closed form
+      kdone = 8 * s0;
+      acc_u = RS_PMIN * s_S[kdone];
+      T = exp2f((float)kdone * RS_LOG2_Q);
+      // brick-space affine form with the padding offset folded in: brick = floor((A - Bk*k) / 8 + PAD)
+      const float Ab[3] = {A[0] * 0.125f + RS_PAD, A[1] * 0.125f + RS_PAD, A[2] * 0.125f + RS_PAD};
+      const float Bb[3] = {Bk[0] * 0.125f, Bk[1] * 0.125f, Bk[2] * 0.125f};
+      for (int s = s0; s < s1; ++s) {
+        const int k = 8 * s + j;
+        const float kf = (float)k;
+        const int X = (int)floorf(fmaf(-Bb[0], kf, Ab[0])), Y = (int)floorf(fmaf(-Bb[1], kf, Ab[1])),
+                  Zb = (int)floorf(fmaf(-Bb[2], kf, Ab[2]));
+        const unsigned hit = (s_occ[(X & 31) * RS_PB + (Y & 31)] >> (Zb & 31)) & 1u;
+        const bool occupied = hit && k < Z && ray_ok;
+        const unsigned m = __ballot_sync(0xffffffffu, occupied);
+        const int kend = min(k - j + 8, Z);
+        if (m == 0) {
+          acc_u = fmaf(RS_PMIN * T, s_cw8[s], acc_u);
+          T *= (kend - (k - j) == 8) ? q8 : exp2f((float)(kend - (k - j)) * RS_LOG2_Q);
+        } else {
+          float p = 0.0f;  // lanes past the end behave like p = 0 (factor 1, no contribution)
+          if (k < Z) {
+            p = RS_PMIN;
+            if (occupied) {
+              float gx, gy, gz;
+              ray_point(dx2, dy2, dz2, k, Z, step, gx, gy, gz);
+              Taps t;
+              make_taps(gx, gy, gz, R, t);
+              p = fminf(fmaxf(sample_trilinear<PRE>(vol, t, R, pre), RS_PMIN), RS_PMAX);
+            }
+          }
+          float incl = 1.0f - p;
+#pragma unroll
+          for (int d = 1; d < 8; d <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, incl, d, 8);
+            if (j >= d) incl *= u;
+          }
+          const float total = __shfl_sync(0xffffffffu, incl, 7, 8);
+          float excl = __shfl_up_sync(0xffffffffu, incl, 1, 8);
+          if (j == 0) excl = 1.0f;
+          if (k < Z) acc = fmaf(p * (T * excl), __ldg(depth_weight + k), acc);
+          T *= total;
+        }
+        kdone = kend;
+        if (__all_sync(0xffffffffu, T == 0.0f)) break;  // every later term of all four rays is exactly 0
+      }
+    }
+    // tail: samples [kdone, Z) in closed form (T == 0 contributes exactly 0)
+    if (kdone < Z) {
+      acc_u = fmaf(RS_PMIN * T, (s_S[Z] - s_S[kdone]) * exp2f(-(float)kdone * RS_LOG2_Q), acc_u);
+      T *= exp2f((float)(Z - kdone) * RS_LOG2_Q);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 8);
+    if (j == 0 && ray_ok) out[(size_t)n * S * S + pix] = acc + acc_u + T;
   }
 }
 
@@ -435,7 +571,7 @@ extern "C" size_t genre_b200_render_spherical_workspace_bytes(int64_t N, int res
 // The same renderer with empty-space skipping (see the header of the skipping section): identical results up to ~1e-6.
 //   use_pre != 0: render clamp(vox * pre_scale, pre_lo, pre_hi) without materialising it
 //   workspace: genre_b200_render_spherical_workspace_bytes(N, res) bytes, caller-owned, zeroed here (memset node)
-// Supported: res % 4 == 0, z_res <= 1024, 16-byte aligned vox; otherwise the call is forwarded to the plain kernel.
+// Supported: res % 4 == 0, res <= 128, z_res <= 1024, 16-byte aligned vox; otherwise the call is forwarded to the plain kernel.
 extern "C" int genre_b200_render_spherical_forward_skip(const float *vox, int64_t N, int res, const double *dirs,
                                                         int sph_res, int z_res, const float *depth_weight, int use_pre,
                                                         float pre_scale, float pre_lo, float pre_hi, float *out,
@@ -444,7 +580,7 @@ extern "C" int genre_b200_render_spherical_forward_skip(const float *vox, int64_
   GB_REQUIRE(out != nullptr, GENRE_B200_EINVAL, "render_spherical: out is null");
   GB_REQUIRE(!use_pre || pre_lo <= pre_hi, GENRE_B200_EINVAL, "render_spherical: empty clamp range");
   const size_t need = genre_b200_render_spherical_workspace_bytes(N, res);
-  const bool can_skip = res % 4 == 0 && z_res <= 32 * RS_MAX_Z_CHUNKS && aligned16(vox) && N < 65536;
+  const bool can_skip = res % 4 == 0 && rs_bricks(res) <= RS_NB_MAX && z_res <= RS_MAX_Z && aligned16(vox) && N < 65536;
   if (!can_skip) {
     if (use_pre) return genre_b200_render_spherical_forward_pre(vox, N, res, dirs, sph_res, z_res, depth_weight, pre_scale, pre_lo, pre_hi, out, stream);
     return genre_b200_render_spherical_forward(vox, N, res, dirs, sph_res, z_res, depth_weight, out, stream);
@@ -455,19 +591,24 @@ extern "C" int genre_b200_render_spherical_forward_skip(const float *vox, int64_
   cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
   if (e != cudaSuccess) return fail_arg((int)e, "render_spherical: cudaMemsetAsync: %s", cudaGetErrorString(e));
   const VoxPre pre = use_pre ? VoxPre{pre_scale, pre_lo, pre_hi} : VoxPre{};
-  const long long v4 = (long long)res * res * res / 4;
-  dim3 og((unsigned)((v4 + 255) / 256), (unsigned)N);
-  if (use_pre) render_occupancy_kernel<true><<<og, 256, 0, st>>>(vox, res, v4, (unsigned *)workspace, pre);
-  else render_occupancy_kernel<false><<<og, 256, 0, st>>>(vox, res, v4, (unsigned *)workspace, pre);
+  if (res == 128) {
+    dim3 og((unsigned)(128 * 128 / (8 * 4)), (unsigned)N);  // 8 warps x 4 rows per CTA
+    if (use_pre) render_occupancy128_kernel<true><<<og, 256, 0, st>>>(vox, (unsigned *)workspace, pre);
+    else render_occupancy128_kernel<false><<<og, 256, 0, st>>>(vox, (unsigned *)workspace, pre);
+  } else {
+    const long long v4 = (long long)res * res * res / 4;
+    dim3 og((unsigned)((v4 + 255) / 256), (unsigned)N);
+    if (use_pre) render_occupancy_kernel<true><<<og, 256, 0, st>>>(vox, res, v4, (unsigned *)workspace, pre);
+    else render_occupancy_kernel<false><<<og, 256, 0, st>>>(vox, res, v4, (unsigned *)workspace, pre);
+  }
   if (int rc = check_launch("render_spherical occupancy kernel")) return rc;
-  const int rays_per_cta = (RS_THREADS / 32) * RS_RAYS_PER_WARP;
+  const int rays_per_cta = (RS_THREADS / 32) * RS_GROUPS_PER_WARP * 4;
   dim3 rg((unsigned)((sph_res * sph_res + rays_per_cta - 1) / rays_per_cta), (unsigned)N);
-  const size_t smem = (size_t)rs_occ_words(res) * 4 + 2 * RS_MAX_Z_CHUNKS * sizeof(float);
   if (use_pre)
-    render_spherical_forward_skip_kernel<true><<<rg, RS_THREADS, smem, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                             (const unsigned *)workspace, out, pre);
+    render_spherical_forward_skip_kernel<true><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
+                                                                          (const unsigned *)workspace, out, pre);
   else
-    render_spherical_forward_skip_kernel<false><<<rg, RS_THREADS, smem, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                              (const unsigned *)workspace, out, pre);
+    render_spherical_forward_skip_kernel<false><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
+                                                                           (const unsigned *)workspace, out, pre);
   return check_launch("render_spherical forward kernel (empty-space skipping)");
 }

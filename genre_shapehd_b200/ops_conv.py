@@ -51,7 +51,7 @@ K4S2_MIN_CIN = 8
 #   "tf32"             single pass, TF32 operands (what cuDNN does while torch.backends.cudnn.allow_tf32 is on)
 # torch.backends.cudnn.allow_tf32 = False upgrades a single-pass mode to "exact" (PyTorch's own switch for fp32 convolutions).
 PRECISION = os.environ.get("GENRE_B200_CONV_PRECISION", "exact")
-EXACT_IMPL = os.environ.get("GENRE_B200_CONV_EXACT_IMPL", "fp32x3")
+EXACT_IMPL = os.environ.get("GENRE_B200_CONV_EXACT_IMPL", "f16x2")
 # k=8 ConvTranspose3d with Cout <= 20 (Unet_3D.dec5): merge the four (y,x) parity classes into one N=80 MMA stream
 MERGE_PARITIES = os.environ.get("GENRE_B200_CONV_MERGE", "1") != "0"
 # Unet_3D.enc1 (4x space-to-depth form): z class on blockIdx.y (N = 80, two CTAs per SM) instead of all 8 classes in N = 160

@@ -208,7 +208,7 @@ def test_tf32_switch_selects_the_fp32_accurate_mode(monkeypatch):
             ref = F.conv_transpose3d(x, m.weight, m.bias, stride=2, padding=1)
         torch.backends.cudnn.allow_tf32 = False
         try:
-            assert ops_conv._mode() == ops_conv.EXACT_IMPL
+            assert ops_conv._mode() == (ops_conv.PRECISION if ops_conv.PRECISION in EXACT_MODES else ops_conv.EXACT_IMPL)
             y = ops_conv.conv_transpose3d(x, m)
             monkeypatch.setattr(ops_conv, "EXACT_WHEN_TF32_OFF", False)
             assert ops_conv.conv_transpose3d(x, m) is None

@@ -395,14 +395,14 @@ def test_render_spherical_skipping_equals_the_plain_kernel(kind):
     plain = torch.empty_like(out)
     _lib.call("genre_b200_render_spherical_forward", vox.data_ptr(), n, res, m._dirs_on(vox.device).data_ptr(), s, z,
               m.depth_weight.data_ptr(), plain.data_ptr(), _lib.stream_ptr(vox))
-    assert (out - plain).abs().max().item() <= 3e-6
+    assert (out - plain).abs().max().item() <= 1e-5     # closed-form q^n against the sample-by-sample fp32 product chain
     # the pre-transform form: clamp(v * 50, 1e-5, 1 - 1e-5) applied on the fly, skipping decided on the transformed values
     raw = vox / 50
     a, b = torch.empty_like(out), torch.empty_like(out)
     render_forward(raw, n, res, m._dirs_on(vox.device), s, z, m.depth_weight, a, pre=(50.0, 1e-5, 1 - 1e-5))
     _lib.call("genre_b200_render_spherical_forward_pre", raw.data_ptr(), n, res, m._dirs_on(vox.device).data_ptr(), s, z,
               m.depth_weight.data_ptr(), 50.0, 1e-5, 1 - 1e-5, b.data_ptr(), _lib.stream_ptr(vox))
-    assert (a - b).abs().max().item() <= 3e-6
+    assert (a - b).abs().max().item() <= 1e-5
 
 
 def test_render_spherical_backward_vs_autograd_of_the_composition():
