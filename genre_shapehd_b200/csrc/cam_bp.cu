@@ -57,14 +57,31 @@ constexpr int PROJ_THREADS = 256;
 constexpr int PROJ_PIX = 4;
 
 // Offsets inside one depth map are 32-bit (checked on the host); only the per-map base is 64-bit.
+struct CamProjArgs {
+  const float *depth;
+  int C, H, W;
+  long long sN, sC;
+  int sH, sW;
+  const float *fl_in;
+  long long fN, fC;
+  const float *cd_in;
+  long long dN, dC;
+  int R;
+  float qscale;
+  VoxWorkspace ws;
+  int fast_shift;
+};
+
+// the project stage of one CTA: pixels [bx * 1024, bx * 1024 + 1024) of map `map`
 template <bool W_FAST>
-__global__ void __launch_bounds__(PROJ_THREADS)
-cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long long sN, long long sC, int sH, int sW,
-                   const float *__restrict__ fl_in, long long fN, long long fC, const float *__restrict__ cd_in,
-                   long long dN, long long dC, int R, float qscale, VoxWorkspace ws, int fast_shift) {
-  extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the splat grid start launching behind us
-  const int map = blockIdx.y;
+__device__ __forceinline__ void cam_project_body(const CamProjArgs &a, int bx, int map, unsigned *s_hist) {
+  const float *__restrict__ depth = a.depth;
+  const float *__restrict__ fl_in = a.fl_in;
+  const float *__restrict__ cd_in = a.cd_in;
+  const int C = a.C, H = a.H, W = a.W, sH = a.sH, sW = a.sW, R = a.R, fast_shift = a.fast_shift;
+  const long long sN = a.sN, sC = a.sC, fN = a.fN, fC = a.fC, dN = a.dN, dC = a.dC;
+  const float qscale = a.qscale;
+  const VoxWorkspace &ws = a.ws;
   int n = map, c = 0;
   if (C != 1) {
     n = map / C;
@@ -92,7 +109,7 @@ cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long lo
     if (!(afl >= 0x1p-40f && afl <= 0x1p40f)) zero_in_bounds = true;  // degenerate focal length: no shortcut
   }
 
-  const int p0 = blockIdx.x * (PROJ_THREADS * PROJ_PIX) + threadIdx.x;
+  const int p0 = bx * (PROJ_THREADS * PROJ_PIX) + threadIdx.x;
   auto coords = [&](int p, int &h, int &w) {
     const int slow = fast_shift >= 0 ? (p >> fast_shift) : (p / fast);
     const int fst = p - slow * fast;
@@ -130,6 +147,22 @@ cam_project_kernel(const float *__restrict__ depth, int C, int H, int W, long lo
   vox_emit<PROJ_PIX, PROJ_THREADS>(gv, q, map, ws, P, s_hist);
 }
 
+template <bool W_FAST>
+__global__ void __launch_bounds__(PROJ_THREADS)
+cam_project_kernel(const CamProjArgs a) {
+  extern __shared__ unsigned s_hist[];  // [ntiles] CTA-local tile histogram
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the splat grid start launching behind us
+  cam_project_body<W_FAST>(a, blockIdx.x, blockIdx.y, s_hist);
+}
+
+template <bool W_FAST>
+struct CamProjector {   // project stage of the pipelined kernel (voxelize.cuh vox_pipeline_kernel)
+  using Args = CamProjArgs;
+  static __device__ __forceinline__ void run(const Args &a, int bx, int map, unsigned *s_hist) {
+    cam_project_body<W_FAST>(a, bx, map, s_hist);
+  }
+};
+
 static int cam_check(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W, const float *fl,
                      const float *camdist, int res) {
   GB_REQUIRE(depth && fl && camdist, GENRE_B200_EINVAL, "cam_bp: null input pointer");
@@ -152,24 +185,34 @@ static inline int log2_exact(int64_t v) {
   return s;
 }
 
+static int cam_proj_args(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN, int64_t sC, int64_t sH,
+                         int64_t sW, const float *fl, int64_t fN, int64_t fC, const float *camdist, int64_t dN, int64_t dC,
+                         int res, const VoxWorkspace &w, CamProjArgs *a, bool *w_fast) {
+  GB_REQUIRE(map_offsets_fit(H, W, sH, sW), GENRE_B200_EINVAL, "cam_bp: depth strides too large");
+  *w_fast = llabs(sW) <= llabs(sH);  // map consecutive threads to the denser image axis
+  a->depth = depth; a->C = (int)C; a->H = (int)H; a->W = (int)W; a->sN = sN; a->sC = sC; a->sH = (int)sH; a->sW = (int)sW;
+  a->fl_in = fl; a->fN = fN; a->fC = fC; a->cd_in = camdist; a->dN = dN; a->dC = dC; a->R = res;
+  a->qscale = (float)res * 16777216.0f;
+  a->ws = w;
+  a->fast_shift = log2_exact(*w_fast ? W : H);
+  return 0;
+}
+
+static inline int cam_proj_ctas_per_map(int64_t P) {
+  const int per_cta = PROJ_THREADS * PROJ_PIX;
+  return (int)((P + per_cta - 1) / per_cta);
+}
+
 static int cam_project_launch(const float *depth, int64_t N, int64_t C, int64_t H, int64_t W, int64_t sN, int64_t sC,
                               int64_t sH, int64_t sW, const float *fl, int64_t fN, int64_t fC, const float *camdist,
                               int64_t dN, int64_t dC, int res, const VoxWorkspace &w, cudaStream_t st) {
-  const int64_t P = H * W;
-  const int per_cta = PROJ_THREADS * PROJ_PIX;
-  dim3 grid((unsigned)((P + per_cta - 1) / per_cta), (unsigned)(N * C));
-  const float qscale = (float)res * 16777216.0f;
-  const bool w_fast = llabs(sW) <= llabs(sH);  // map consecutive threads to the denser image axis
+  CamProjArgs a;
+  bool w_fast = true;
+  if (int rc = cam_proj_args(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, &a, &w_fast)) return rc;
+  dim3 grid((unsigned)cam_proj_ctas_per_map(H * W), (unsigned)(N * C));
   const size_t smem = (size_t)w.ntiles * 4;
-  GB_REQUIRE(map_offsets_fit(H, W, sH, sW), GENRE_B200_EINVAL, "cam_bp: depth strides too large");
-  if (w_fast)
-    cam_project_kernel<true><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, (int)sH, (int)sW,
-                                                              fl, fN, fC, camdist, dN, dC, res, qscale, w,
-                                                              log2_exact(W));
-  else
-    cam_project_kernel<false><<<grid, PROJ_THREADS, smem, st>>>(depth, (int)C, (int)H, (int)W, sN, sC, (int)sH,
-                                                               (int)sW, fl, fN, fC, camdist, dN, dC, res, qscale, w,
-                                                               log2_exact(H));
+  if (w_fast) cam_project_kernel<true><<<grid, PROJ_THREADS, smem, st>>>(a);
+  else cam_project_kernel<false><<<grid, PROJ_THREADS, smem, st>>>(a);
   return check_launch("cam_bp project kernel");
 }
 
@@ -353,6 +396,17 @@ extern "C" int genre_b200_cam_bp_forward(const float *depth, int64_t N, int64_t 
     bg = inv_r;
   }
   if (int rc = vox_clear_counts(w, N * C, st)) return rc;
+  if (!(flags & GENRE_B200_FLAG_NO_PIPELINE)) {
+    // batches of 4+ maps: chunked project|splat pipeline (voxelize.cuh): the next chunk's projection hides under the
+    // streaming stores of the previous one
+    CamProjArgs a;
+    bool w_fast = true;
+    if (int rc = cam_proj_args(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, &a, &w_fast)) return rc;
+    const int gx = cam_proj_ctas_per_map(H * W);
+    const int rc = w_fast ? vox_pipeline<CamProjector<true>>(a, gx, w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st)
+                          : vox_pipeline<CamProjector<false>>(a, gx, w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st);
+    if (rc >= 0) return rc;
+  }
   if (int rc = cam_project_launch(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, st)) return rc;
   return vox_splat(w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st);
 }

@@ -178,7 +178,7 @@ constexpr int RS_BRICK = 8;
 constexpr int RS_NB_MAX = 16;         // bricks per dimension the padded mask covers (res <= 128)
 constexpr int RS_PAD = 8;             // padding bricks on each side: |coord| <= 2  ->  brick index in [-8, 24)
 constexpr int RS_PB = 32;             // padded bricks per dimension
-constexpr int RS_GROUPS_PER_WARP = 4; // 4-ray groups a warp walks one after the other (16 rays per warp, 128 per CTA)
+constexpr int RS_CTAS_PER_VOLUME = 40; // persistent CTAs per volume; their warps draw 4-ray groups from a per-volume counter
 constexpr int RS_MAX_Z = 1024;
 constexpr float RS_LOG2_Q = -1.4427022e-05f;  // log2(1 - 1e-5)
 
@@ -268,10 +268,9 @@ template <bool PRE>
 __global__ void __launch_bounds__(RS_THREADS)
 render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const double *__restrict__ dirs, int S, int Z,
                                      const float *__restrict__ depth_weight, const unsigned *__restrict__ occ,
-                                     float *__restrict__ out, const VoxPre pre) {
+                                     unsigned *__restrict__ group_counter, float *__restrict__ out, const VoxPre pre) {
   __shared__ unsigned s_occ[RS_PB * RS_PB];  // padded brick mask: word = X * 32 + Y, bit = Z (padded brick coordinates)
   __shared__ float s_S[RS_MAX_Z + 1];        // S[k] = sum_{j<k} q^j w_j
-  __shared__ float s_cw8[RS_MAX_Z / 8];      // sum_{j<8} q^j w_{8s+j}
   __shared__ int s_box[6];                   // marked-brick bounding box: min x,y,z, max x,y,z (unpadded brick coordinates)
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = rs_bricks(R), words = rs_occ_words(R);
@@ -313,10 +312,6 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
       atomicMax(&s_box[3], bx); atomicMax(&s_box[4], by); atomicMax(&s_box[5], bz);
     }
   }
-  for (int s8 = tid; s8 * 8 < Z; s8 += RS_THREADS) {
-    const int a = s8 * 8, b = min(a + 8, Z);
-    s_cw8[s8] = (s_S[b] - s_S[a]) * exp2f(-(float)a * RS_LOG2_Q);
-  }
   __syncthreads();
   const bool any = s_box[3] >= 0;
   // sample-space box: a sample looks up brick floor(f / 8) (f in [-8, 0) finds the copies of boundary marks)
@@ -331,14 +326,17 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
   const float *vol = vox + (size_t)n * R * R * R;
   const int j = lane & 7, grp = lane >> 3;
   const int nsteps = (Z + 7) / 8;
-  const float q8 = exp2f(8.0f * RS_LOG2_Q);
-  for (int gi = 0; gi < RS_GROUPS_PER_WARP; ++gi) {
-    const int pix_base = ((blockIdx.x * (RS_THREADS / 32) + warp) * RS_GROUPS_PER_WARP + gi) * 4;
-    if (pix_base >= S * S) break;  // warp-uniform
-    const int pix = pix_base + grp;
+  const int ngroups = (S * S + 3) / 4;
+  // 4-ray groups are handed out dynamically (rays that cross the shell cost ~10x the others): one counter per volume
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = (int)atomicAdd(group_counter + n, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups) break;
+    const int pix = g * 4 + grp;
     const bool ray_ok = pix < S * S;
     const int pixc = ray_ok ? pix : S * S - 1;
-    const double dx = dirs[pixc * 3 + 0], dy = dirs[pixc * 3 + 1], dz = dirs[pixc * 3 + 2];
+    const double dx = __ldg(dirs + pixc * 3 + 0), dy = __ldg(dirs + pixc * 3 + 1), dz = __ldg(dirs + pixc * 3 + 2);
     const double dx2 = dx * 2.0, dy2 = dy * 2.0, dz2 = dz * 2.0;
     // voxel coordinate of sample k (fp32 estimate): f = h + d*h*2*(1 - k*step) = A - Bk * k
     const float A[3] = {h + 2.0f * (float)dx * h, h + 2.0f * (float)dy * h, h + 2.0f * (float)dz * h};
@@ -349,7 +347,7 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       if (fabsf(Bk[d]) > 1e-12f) {
-        const float inv = 1.0f / Bk[d];
+        const float inv = __frcp_rn(Bk[d]);
         const float k1 = (A[d] - blo[d]) * inv, k2 = (A[d] - bhi[d]) * inv;
         kmin = fmaxf(kmin, fminf(k1, k2));
         kmax = fminf(kmax, fmaxf(k1, k2));
@@ -367,53 +365,59 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
     s1 = __reduce_max_sync(0xffffffffu, s1);
     float T = 1.0f, acc = 0.0f, acc_u = 0.0f;
     int kdone = 0;  // samples [0, kdone) are accounted for
-    if (s0 < s1) {
-      // head: samples [0, 8*s0) in closed form
-      kdone = 8 * s0;
-      acc_u = RS_PMIN * s_S[kdone];
-      T = exp2f((float)kdone * RS_LOG2_Q);
-      // brick-space affine form with the padding offset folded in: brick = floor((A - Bk*k) / 8 + PAD)
-      const float Ab[3] = {A[0] * 0.125f + RS_PAD, A[1] * 0.125f + RS_PAD, A[2] * 0.125f + RS_PAD};
-      const float Bb[3] = {Bk[0] * 0.125f, Bk[1] * 0.125f, Bk[2] * 0.125f};
-      for (int s = s0; s < s1; ++s) {
+    // phase A: occupancy of every sample of every candidate step, independent iterations (the loads and conversions of
+    // several steps are in flight together); windows of 32 steps
+    const float Ab[3] = {A[0] * 0.125f + RS_PAD, A[1] * 0.125f + RS_PAD, A[2] * 0.125f + RS_PAD};
+    const float Bb[3] = {Bk[0] * 0.125f, Bk[1] * 0.125f, Bk[2] * 0.125f};
+    for (int w0 = s0; w0 < s1; w0 += 32) {   // warp-uniform bounds (ballots inside)
+      const int w1 = min(w0 + 32, s1);
+      unsigned mine = 0;       // bit i: this lane's sample of step w0 + i is occupied
+      unsigned steps_any = 0;  // bit i: some lane's sample of step w0 + i is occupied (warp-uniform)
+#pragma unroll 4
+      for (int s = w0; s < w1; ++s) {
         const int k = 8 * s + j;
         const float kf = (float)k;
         const int X = (int)floorf(fmaf(-Bb[0], kf, Ab[0])), Y = (int)floorf(fmaf(-Bb[1], kf, Ab[1])),
                   Zb = (int)floorf(fmaf(-Bb[2], kf, Ab[2]));
-        const unsigned hit = (s_occ[(X & 31) * RS_PB + (Y & 31)] >> (Zb & 31)) & 1u;
-        const bool occupied = hit && k < Z && ray_ok;
-        const unsigned m = __ballot_sync(0xffffffffu, occupied);
-        const int kend = min(k - j + 8, Z);
-        if (m == 0) {
-          acc_u = fmaf(RS_PMIN * T, s_cw8[s], acc_u);
-          T *= (kend - (k - j) == 8) ? q8 : exp2f((float)(kend - (k - j)) * RS_LOG2_Q);
-        } else {
-          float p = 0.0f;  // lanes past the end behave like p = 0 (factor 1, no contribution)
-          if (k < Z) {
-            p = RS_PMIN;
-            if (occupied) {
-              float gx, gy, gz;
-              ray_point(dx2, dy2, dz2, k, Z, step, gx, gy, gz);
-              Taps t;
-              make_taps(gx, gy, gz, R, t);
-              p = fminf(fmaxf(sample_trilinear<PRE>(vol, t, R, pre), RS_PMIN), RS_PMAX);
-            }
-          }
-          float incl = 1.0f - p;
-#pragma unroll
-          for (int d = 1; d < 8; d <<= 1) {
-            const float u = __shfl_up_sync(0xffffffffu, incl, d, 8);
-            if (j >= d) incl *= u;
-          }
-          const float total = __shfl_sync(0xffffffffu, incl, 7, 8);
-          float excl = __shfl_up_sync(0xffffffffu, incl, 1, 8);
-          if (j == 0) excl = 1.0f;
-          if (k < Z) acc = fmaf(p * (T * excl), __ldg(depth_weight + k), acc);
-          T *= total;
-        }
-        kdone = kend;
-        if (__all_sync(0xffffffffu, T == 0.0f)) break;  // every later term of all four rays is exactly 0
+        const bool occupied = ((s_occ[(X & 31) * RS_PB + (Y & 31)] >> (Zb & 31)) & 1u) && k < Z && ray_ok;
+        mine |= (unsigned)occupied << (s - w0);
+        steps_any |= (__ballot_sync(0xffffffffu, occupied) ? 1u : 0u) << (s - w0);
       }
+      // phase B: jump from occupied step to occupied step
+      while (steps_any) {
+        const int i = __ffs(steps_any) - 1;
+        steps_any &= steps_any - 1;
+        const int s = w0 + i, kstart = 8 * s, k = kstart + j;
+        if (kstart > kdone) {  // the empty run [kdone, kstart) in closed form
+          acc_u = fmaf(RS_PMIN * T, (s_S[kstart] - s_S[kdone]) * exp2f(-(float)kdone * RS_LOG2_Q), acc_u);
+          T *= exp2f((float)(kstart - kdone) * RS_LOG2_Q);
+        }
+        float p = 0.0f;  // lanes past the end behave like p = 0 (factor 1, no contribution)
+        if (k < Z) {
+          p = RS_PMIN;
+          if ((mine >> i) & 1u) {
+            float gx, gy, gz;
+            ray_point(dx2, dy2, dz2, k, Z, step, gx, gy, gz);
+            Taps t;
+            make_taps(gx, gy, gz, R, t);
+            p = fminf(fmaxf(sample_trilinear<PRE>(vol, t, R, pre), RS_PMIN), RS_PMAX);
+          }
+        }
+        float incl = 1.0f - p;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+          const float u = __shfl_up_sync(0xffffffffu, incl, d, 8);
+          if (j >= d) incl *= u;
+        }
+        const float total = __shfl_sync(0xffffffffu, incl, 7, 8);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1, 8);
+        if (j == 0) excl = 1.0f;
+        if (k < Z) acc = fmaf(p * (T * excl), __ldg(depth_weight + k), acc);
+        T *= total;
+        kdone = min(kstart + 8, Z);
+        if (__all_sync(0xffffffffu, T == 0.0f)) { steps_any = 0; }  // every later term of all four rays is exactly 0
+      }
+      if (__all_sync(0xffffffffu, T == 0.0f)) break;
     }
     // tail: samples [kdone, Z) in closed form (T == 0 contributes exactly 0)
     if (kdone < Z) {
@@ -565,7 +569,7 @@ extern "C" int genre_b200_render_spherical_backward(const float *vox, int64_t N,
 
 extern "C" size_t genre_b200_render_spherical_workspace_bytes(int64_t N, int res) {
   if (N <= 0 || res < 2) return 0;
-  return (size_t)N * rs_occ_words(res) * sizeof(unsigned);
+  return ((size_t)N * rs_occ_words(res) + (size_t)N) * sizeof(unsigned);   // brick masks + one work counter per volume
 }
 
 // The same renderer with empty-space skipping (see the header of the skipping section): identical results up to ~1e-6.
@@ -602,13 +606,15 @@ extern "C" int genre_b200_render_spherical_forward_skip(const float *vox, int64_
     else render_occupancy_kernel<false><<<og, 256, 0, st>>>(vox, res, v4, (unsigned *)workspace, pre);
   }
   if (int rc = check_launch("render_spherical occupancy kernel")) return rc;
-  const int rays_per_cta = (RS_THREADS / 32) * RS_GROUPS_PER_WARP * 4;
-  dim3 rg((unsigned)((sph_res * sph_res + rays_per_cta - 1) / rays_per_cta), (unsigned)N);
+  unsigned *counters = (unsigned *)workspace + (size_t)N * rs_occ_words(res);
+  const int ngroups = (sph_res * sph_res + 3) / 4;
+  const int ctas = ngroups < RS_CTAS_PER_VOLUME * (RS_THREADS / 32) ? (ngroups + RS_THREADS / 32 - 1) / (RS_THREADS / 32) : RS_CTAS_PER_VOLUME;
+  dim3 rg((unsigned)ctas, (unsigned)N);
   if (use_pre)
     render_spherical_forward_skip_kernel<true><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                          (const unsigned *)workspace, out, pre);
+                                                                          (const unsigned *)workspace, counters, out, pre);
   else
     render_spherical_forward_skip_kernel<false><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                           (const unsigned *)workspace, out, pre);
+                                                                           (const unsigned *)workspace, counters, out, pre);
   return check_launch("render_spherical forward kernel (empty-space skipping)");
 }

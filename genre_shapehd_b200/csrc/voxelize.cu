@@ -44,111 +44,11 @@ int vox_clear_counts(const VoxWorkspace &w, int64_t n_maps, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // splat: one CTA per output tile
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float vox_finalize(unsigned lo, unsigned hi, float alpha, float beta, float bg,
-                                              float &count_out) {
-  const unsigned c = hi >> 12;
-  count_out = (float)c;
-  if (c == 0) return bg;
-  const unsigned long long sum = ((unsigned long long)(hi & 0xFFFu) << 32) | lo;
-  return fmaf(beta, __ull2float_rn(sum) / (float)c, alpha);
-}
-
-constexpr int SPLAT_KEEP = VOX_BUCKET / VOX_SPLAT_THREADS;  // the whole bucket fits in registers (4 records/thread)
-
 template <bool VEC, bool WRITE_CNT>
 __global__ void __launch_bounds__(VOX_SPLAT_THREADS)
-vox_splat_kernel(const uint2 *__restrict__ buckets, const uint2 *__restrict__ ovf,
-                 const unsigned *__restrict__ counts, const unsigned *__restrict__ ovf_count,
-                 float *__restrict__ tdf, float *__restrict__ cnt, long long P, long long nvox, int ntiles,
-                 float alpha, float beta, float bg, long long out_stride) {
-  __shared__ __align__(16) unsigned s_lo[VOX_TILE];
-  __shared__ __align__(16) unsigned s_hi[VOX_TILE];
-  const int tile = blockIdx.x, map = blockIdx.y, tid = threadIdx.x;
-  const size_t tix = (size_t)map * ntiles + tile;
-  // Programmatic dependent launch: this grid may become resident while the project kernel drains; nothing the
-  // project kernel wrote is read before this point.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const unsigned n = counts[tix];
-  const long long start = (long long)tile * VOX_TILE;
-  const int nv = (int)min((long long)VOX_TILE, nvox - start);
-  float *out = tdf + (size_t)map * out_stride + start;  // out_stride > nvox: a channel of a wider tensor
-  float *cout = WRITE_CNT ? cnt + (size_t)map * nvox + start : nullptr;
-
-  if (n == 0) {  // background-only tile: pure streaming fill, no shared memory touched
-    if (VEC) {
-      const float4 b4 = make_float4(bg, bg, bg, bg), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = tid * 4; j < VOX_TILE; j += VOX_SPLAT_THREADS * 4) {
-        if (j < nv) {
-          st_stream_f4(out + j, b4);
-          if (WRITE_CNT) st_stream_f4(cout + j, z4);
-        }
-      }
-    } else {
-      for (int j = tid; j < nv; j += VOX_SPLAT_THREADS) {
-        st_stream_f1(out + j, bg);
-        if (WRITE_CNT) st_stream_f1(cout + j, 0.f);
-      }
-    }
-    return;
-  }
-
-  // the bucket is fetched before the accumulators are cleared so the load latency overlaps the clearing
-  const uint2 *seg = buckets + tix * VOX_BUCKET;
-  const unsigned nb = min(n, (unsigned)VOX_BUCKET);
-  uint2 r[SPLAT_KEEP];
-#pragma unroll
-  for (int k = 0; k < SPLAT_KEEP; ++k) {
-    const unsigned i = tid + k * VOX_SPLAT_THREADS;
-    r[k] = i < nb ? seg[i] : make_uint2(0, 0);
-  }
-#pragma unroll
-  for (int j = tid * 4; j < VOX_TILE; j += VOX_SPLAT_THREADS * 4) {
-    *reinterpret_cast<uint4 *>(s_lo + j) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4 *>(s_hi + j) = make_uint4(0, 0, 0, 0);
-  }
-  __syncthreads();
-  auto add = [&](unsigned v, unsigned q) {
-    const unsigned old = atomicAdd(&s_lo[v], q);
-    const unsigned carry = (old + q < old) ? 1u : 0u;
-    atomicAdd(&s_hi[v], (1u << 12) + carry);
-  };
-#pragma unroll
-  for (int k = 0; k < SPLAT_KEEP; ++k)
-    if (tid + k * VOX_SPLAT_THREADS < nb) add(r[k].x, r[k].y);
-  if (n > (unsigned)VOX_BUCKET) {  // CTA-uniform, rare: this tile spilled; pick its records out of the map's list
-    const unsigned novf = ovf_count[map];
-    const uint2 *list = ovf + (size_t)map * P;
-    for (unsigned i = tid; i < novf; i += VOX_SPLAT_THREADS) {
-      const uint2 x = list[i];
-      if (x.x / VOX_TILE == (unsigned)tile) add(x.x - tile * VOX_TILE, x.y);
-    }
-  }
-  __syncthreads();
-
-  if (VEC) {
-#pragma unroll
-    for (int j = tid * 4; j < VOX_TILE; j += VOX_SPLAT_THREADS * 4) {
-      if (j < nv) {
-        const uint4 lo = *reinterpret_cast<const uint4 *>(s_lo + j);
-        const uint4 hi = *reinterpret_cast<const uint4 *>(s_hi + j);
-        float4 o, c;
-        o.x = vox_finalize(lo.x, hi.x, alpha, beta, bg, c.x);
-        o.y = vox_finalize(lo.y, hi.y, alpha, beta, bg, c.y);
-        o.z = vox_finalize(lo.z, hi.z, alpha, beta, bg, c.z);
-        o.w = vox_finalize(lo.w, hi.w, alpha, beta, bg, c.w);
-        st_stream_f4(out + j, o);
-        if (WRITE_CNT) st_stream_f4(cout + j, c);
-      }
-    }
-  } else {
-    for (int j = tid; j < nv; j += VOX_SPLAT_THREADS) {
-      float c;
-      const float o = vox_finalize(s_lo[j], s_hi[j], alpha, beta, bg, c);
-      st_stream_f1(out + j, o);
-      if (WRITE_CNT) st_stream_f1(cout + j, c);
-    }
-  }
+vox_splat_kernel(const SplatArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  vox_splat_body<VEC, WRITE_CNT>(a, blockIdx.x, blockIdx.y);
 }
 
 template <bool VEC, bool WRITE_CNT>
@@ -164,12 +64,8 @@ static int launch_splat(const VoxWorkspace &w, int64_t n_maps, int64_t P, long l
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;  // stand-alone launches (stage entry point, used for timing) keep plain stream ordering
-  const uint2 *buckets = w.buckets, *ovf = w.ovf;
-  const unsigned *counts = w.counts, *ovf_count = w.ovf_count;
-  const long long Pll = (long long)P;
-  const int ntiles = w.ntiles;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, vox_splat_kernel<VEC, WRITE_CNT>, buckets, ovf, counts, ovf_count, tdf, cnt,
-                                     Pll, nvox, ntiles, alpha, beta, bg, out_stride);
+  const SplatArgs a = vox_splat_args(w, P, nvox, tdf, cnt, alpha, beta, bg, out_stride);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, vox_splat_kernel<VEC, WRITE_CNT>, a);
   if (e != cudaSuccess) {
     set_error("voxelize splat kernel: %s", cudaGetErrorString(e));
     cudaGetLastError();

@@ -203,10 +203,13 @@ def test_shapehd_training_step_runs_on_cuda(ref_root):
     loss_r, g_r = step(False)
     assert np.isfinite(loss_c) and abs(loss_c - loss_r) <= 1e-4 * max(1.0, abs(loss_r))
     assert g_c.keys() == g_r.keys() and len(g_c) >= 10
+    overall = max(v.abs().max().item() for v in g_r.values())
     for name in g_c:
-        scale = g_r[name].abs().max().item() + 1e-12
+        scale = g_r[name].abs().max().item()
         # two fp32 implementations with different summation orders, through training-mode BatchNorm at batch 2 and the BCE's
-        # cancellation: the first layers' weight gradients (~5e-4) agree to a few 1e-3 of their scale
-        assert (g_c[name] - g_r[name]).abs().max().item() <= 1e-2 * scale, name
+        # cancellation: weight gradients agree to a few 1e-3 of their scale.  The bias of a convolution that feeds a
+        # training-mode BatchNorm has an exactly-zero gradient (the mean is subtracted): both sides hold rounding noise there,
+        # hence the absolute floor.
+        assert (g_c[name] - g_r[name]).abs().max().item() <= 1e-2 * scale + 1e-6 * overall, name
     for p in net.d.parameters():
         assert p.grad is None            # D stays frozen (shapehd.py:104-105)
