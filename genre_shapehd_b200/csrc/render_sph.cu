@@ -38,12 +38,17 @@ __device__ __forceinline__ void make_taps(float gx, float gy, float gz, int R, T
   const float wx1 = fx - x0f, wx0 = (x0f + 1.0f) - fx;
   const float wy1 = fy - y0f, wy0 = (y0f + 1.0f) - fy;
   const float wz1 = fz - z0f, wz0 = (z0f + 1.0f) - fz;
-  const bool vx0 = (unsigned)x0 < (unsigned)R, vx1 = (unsigned)(x0 + 1) < (unsigned)R;
-  const bool vy0 = (unsigned)y0 < (unsigned)R, vy1 = (unsigned)(y0 + 1) < (unsigned)R;
-  const bool vz0 = (unsigned)z0 < (unsigned)R, vz1 = (unsigned)(z0 + 1) < (unsigned)R;
   t.base = (x0 * R + y0) * R + z0;
   t.w[0] = wx0 * wy0 * wz0; t.w[1] = wx0 * wy0 * wz1; t.w[2] = wx0 * wy1 * wz0; t.w[3] = wx0 * wy1 * wz1;
   t.w[4] = wx1 * wy0 * wz0; t.w[5] = wx1 * wy0 * wz1; t.w[6] = wx1 * wy1 * wz0; t.w[7] = wx1 * wy1 * wz1;
+  const unsigned Rm = (unsigned)(R - 1);
+  if (((unsigned)x0 < Rm) & ((unsigned)y0 < Rm) & ((unsigned)z0 < Rm)) {  // all 8 taps inside: the common case
+    t.valid = 0xFFu;
+    return;
+  }
+  const bool vx0 = (unsigned)x0 < (unsigned)R, vx1 = (unsigned)(x0 + 1) < (unsigned)R;
+  const bool vy0 = (unsigned)y0 < (unsigned)R, vy1 = (unsigned)(y0 + 1) < (unsigned)R;
+  const bool vz0 = (unsigned)z0 < (unsigned)R, vz1 = (unsigned)(z0 + 1) < (unsigned)R;
   t.valid = (unsigned)(vx0 & vy0 & vz0) | ((unsigned)(vx0 & vy0 & vz1) << 1) | ((unsigned)(vx0 & vy1 & vz0) << 2) |
             ((unsigned)(vx0 & vy1 & vz1) << 3) | ((unsigned)(vx1 & vy0 & vz0) << 4) |
             ((unsigned)(vx1 & vy0 & vz1) << 5) | ((unsigned)(vx1 & vy1 & vz0) << 6) |
@@ -164,23 +169,23 @@ render_spherical_forward_kernel(const float *__restrict__ vox, int R, const doub
 // p = 1e-5 (up to a 1e-12 rounding of the interpolation), and a run of such samples has a closed form:
 //     T after n samples = T * q^n,     sum_k s_k w_k over the run = 1e-5 * T * (S[b] - S[a]) / q^a,
 //     q = 1 - 1e-5,   S[k] = sum_{j<k} q^j w_j  (prefix table built per CTA from the caller's depth_weight buffer).
-//   pre-pass  (render_occupancy_*): one read of the volume -> a bit per 8^3 brick b, set when any voxel in [8b-1, 8b+9]
+//   pre-pass  (render_occupancy_*): one read of the volume -> a bit per 4^3 brick b, set when any voxel in [4b-1, 4b+5]
 //             per dimension exceeds 1e-5: a sample at voxel coordinate f reads taps floor(f), floor(f)+1, so the brick
-//             floor(f/8) covers both (+8), the -1 / +9 absorb the fp32 estimate of f used for the lookup;
+//             floor(f/4) covers both (+4), the -1 / +5 absorb the fp32 estimate of f used for the lookup;
 //   render    a warp owns 4 neighbouring rays x 8 consecutive samples per step.  The bounding box of the marked bricks
 //             gives each ray a sample range [K0, K1): everything before and after it is ONE closed-form update.  Inside,
-//             every lane looks its sample's brick up in a 32^3-brick padded bitmask in shared memory (3 FMAs + 3 floors:
+//             every lane looks its sample's brick up in a 64^3-brick padded bitmask in shared memory (32 KB) (3 FMAs + 3 floors:
 //             positions anywhere in [-2, 2]^3 index it without range checks); a step whose 32 samples are all empty is a
 //             closed-form update, otherwise the lanes on occupied bricks take the exact path (fp64 positions, 8 taps) and the
 //             transmittance is scanned inside each 8-lane group.
 // Error against the sample-by-sample product: a few 1e-7 relative on T (measured <= 4e-6 on the output).
-constexpr int RS_BRICK = 8;
-constexpr int RS_NB_MAX = 16;         // bricks per dimension the padded mask covers (res <= 128)
-constexpr int RS_PAD = 8;             // padding bricks on each side: |coord| <= 2  ->  brick index in [-8, 24)
-constexpr int RS_PB = 32;             // padded bricks per dimension
-constexpr int RS_CTAS_PER_VOLUME = 40; // persistent CTAs per volume; their warps draw 4-ray groups from a per-volume counter
+constexpr int RS_BRICK = 4;
+constexpr int RS_NB_MAX = 32;         // bricks per dimension the padded mask covers (res <= 128)
+constexpr int RS_PAD = 16;            // padding bricks on each side: |coord| <= 2  ->  brick index in [-16, 48)
+constexpr int RS_PB = 64;             // padded bricks per dimension
 constexpr int RS_MAX_Z = 1024;
 constexpr float RS_LOG2_Q = -1.4427022e-05f;  // log2(1 - 1e-5)
+constexpr float RS_INV_BRICK = 1.0f / RS_BRICK;
 
 __host__ __device__ inline int rs_bricks(int R) { return (R + RS_BRICK - 1) / RS_BRICK; }
 __host__ __device__ inline int rs_occ_words(int R) {
@@ -211,7 +216,7 @@ render_occupancy_kernel(const float *__restrict__ vox, int R, long long vox_per_
   const long long lin = i4 * 4;
   const int z = (int)(lin % R), y = (int)((lin / R) % R), x = (int)(lin / ((long long)R * R));
   const int nb = rs_bricks(R);
-  // brick b is marked iff an occupied voxel lies in [8b - 1, 8b + 9]  <=>  b in [floor((v - 2) / 8), floor((v + 1) / 8)]
+  // brick b is marked iff an occupied voxel lies in [4b - 1, 4b + 5]  <=>  b in [floor((v - 2) / 4), floor((v + 1) / 4)]
   const int bx0 = max(x - 2, 0) / RS_BRICK, bx1 = min(x + 1, R - 1) / RS_BRICK;
   const int by0 = max(y - 2, 0) / RS_BRICK, by1 = min(y + 1, R - 1) / RS_BRICK;
   const int bz0 = max(z + zlo - 2, 0) / RS_BRICK, bz1 = min(z + zhi + 1, R - 1) / RS_BRICK;
@@ -225,12 +230,13 @@ render_occupancy_kernel(const float *__restrict__ vox, int R, long long vox_per_
       }
 }
 
-// R = 128 pre-pass: a warp owns whole z rows (32 lanes x 4 voxels = 128), 4 rows in flight per iteration; a row's 16 z-brick
+// R = 128 pre-pass: a warp owns whole z rows (32 lanes x 4 voxels = 128), 4 rows in flight per iteration; a row's 32 z-brick
 // bits are OR-reduced across the warp and merged into the (at most 2 x 2) brick columns its dilated (x, y) touches.
 template <bool PRE>
 __global__ void __launch_bounds__(256)
 render_occupancy128_kernel(const float *__restrict__ vox, unsigned *__restrict__ occ, const VoxPre pre) {
-  constexpr int R = 128, ROWS = 4;
+  constexpr int R = 128, ROWS = 4, NB = R / RS_BRICK;
+  static_assert(NB == 32, "one 32-bit word per (bx, by) brick column");
   const int n = blockIdx.y, lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int row0 = warp_global * ROWS;  // row index = x * R + y
@@ -249,18 +255,16 @@ render_occupancy128_kernel(const float *__restrict__ vox, unsigned *__restrict__
       const float t = PRE ? fminf(fmaxf(__fmul_rn(a[i], pre.scale), pre.lo), pre.hi) : a[i];
       if (!(t <= RS_PMIN)) {
         const int z = lane * 4 + i;
-        zmask |= (1u << (max(z - 2, 0) >> 3)) | (1u << (min(z + 1, R - 1) >> 3));
+        zmask |= (1u << (max(z - 2, 0) / RS_BRICK)) | (1u << (min(z + 1, R - 1) / RS_BRICK));
       }
     }
     zmask = __reduce_or_sync(0xffffffffu, zmask);
     if (zmask == 0 || lane >= 4) continue;
     const int row = row0 + r, x = row >> 7, y = row & 127;
-    const int bx = (lane & 1) ? min(x + 1, R - 1) >> 3 : max(x - 2, 0) >> 3;
-    const int by = (lane & 2) ? min(y + 1, R - 1) >> 3 : max(y - 2, 0) >> 3;
-    // bit = (bx*16 + by)*16 + bz: word = bx*8 + (by >> 1), the row's 16 bits at (by & 1) * 16
-    unsigned *w = o + bx * 8 + (by >> 1);
-    const unsigned m = zmask << ((by & 1) * 16);
-    if ((*w & m) != m) atomicOr(w, m);
+    const int bx = ((lane & 1) ? min(x + 1, R - 1) : max(x - 2, 0)) / RS_BRICK;
+    const int by = ((lane & 2) ? min(y + 1, R - 1) : max(y - 2, 0)) / RS_BRICK;
+    unsigned *w = o + bx * NB + by;   // bit = (bx*32 + by)*32 + bz: one word per brick column
+    if ((*w & zmask) != zmask) atomicOr(w, zmask);
   }
 }
 
@@ -268,13 +272,12 @@ template <bool PRE>
 __global__ void __launch_bounds__(RS_THREADS)
 render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const double *__restrict__ dirs, int S, int Z,
                                      const float *__restrict__ depth_weight, const unsigned *__restrict__ occ,
-                                     unsigned *__restrict__ group_counter, float *__restrict__ out, const VoxPre pre) {
-  __shared__ unsigned s_occ[RS_PB * RS_PB];  // padded brick mask: word = X * 32 + Y, bit = Z (padded brick coordinates)
-  __shared__ float s_S[RS_MAX_Z + 1];        // S[k] = sum_{j<k} q^j w_j
-  __shared__ int s_box[6];                   // marked-brick bounding box: min x,y,z, max x,y,z (unpadded brick coordinates)
+                                     float *__restrict__ out, const VoxPre pre) {
+  __shared__ unsigned long long s_occ[RS_PB * RS_PB];  // padded brick mask: word = X * 64 + Y, bit = Z (padded brick coordinates)
+  __shared__ float s_S[RS_MAX_Z + 1];                  // S[k] = sum_{j<k} q^j w_j
+  __shared__ int s_box[6];                             // marked-brick bounding box: min x,y,z, max x,y,z (unpadded)
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = rs_bricks(R), words = rs_occ_words(R);
-  for (int i = tid; i < RS_PB * RS_PB; i += RS_THREADS) s_occ[i] = 0;
   if (tid < 3) s_box[tid] = nb;
   else if (tid < 6) s_box[tid] = -1;
   // prefix table of q^j w_j: warp 0, 32 entries per pass
@@ -295,31 +298,39 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
     if (lane == 0) s_S[0] = 0.0f;
   }
   __syncthreads();
-  // expand the compact mask into the padded one and take its bounding box
-  for (int wi = tid; wi < words; wi += RS_THREADS) {
-    const unsigned wv = occ[(size_t)n * words + wi];
-    if (!wv) continue;
-    for (unsigned rem = wv; rem;) {
-      const int b = __ffs(rem) - 1;
-      rem &= rem - 1;
-      const int bit = wi * 32 + b;
-      const int bz = bit % nb, by = (bit / nb) % nb, bx = bit / (nb * nb);
-      // f in (-1, 0) reads voxel 0 but floors to brick -1: a marked boundary brick also marks its outside neighbour(s)
-      const unsigned zb = (1u << (bz + RS_PAD)) | (bz == 0 ? 1u << (RS_PAD - 1) : 0u);
-      for (int ex = (bx == 0 ? -1 : 0); ex <= 0; ++ex)
-        for (int ey = (by == 0 ? -1 : 0); ey <= 0; ++ey) atomicOr(&s_occ[(bx + ex + RS_PAD) * RS_PB + (by + ey + RS_PAD)], zb);
-      atomicMin(&s_box[0], bx); atomicMin(&s_box[1], by); atomicMin(&s_box[2], bz);
-      atomicMax(&s_box[3], bx); atomicMax(&s_box[4], by); atomicMax(&s_box[5], bz);
+  // padded mask: thread-owned words (no atomics).  Padded column (X, Y) holds brick column (X - PAD, Y - PAD); a sample with
+  // f in (-1, 0) reads voxel 0 but floors to brick -1, so column -1 (and bit -1) copy column 0 (bit 0).
+  const unsigned *cocc = occ + (size_t)n * words;
+  for (int wi = tid; wi < RS_PB * RS_PB; wi += RS_THREADS) {
+    int bx = wi / RS_PB - RS_PAD, by = wi % RS_PB - RS_PAD;
+    const bool own = bx >= 0 && by >= 0;      // not a boundary copy: contributes to the bounding box
+    if (bx == -1) bx = 0;
+    if (by == -1) by = 0;
+    unsigned long long row = 0;
+    if (bx >= 0 && bx < nb && by >= 0 && by < nb) {
+      const int bit0 = (bx * nb + by) * nb;   // nb <= 32 consecutive bits of the compact mask
+      const int w0 = bit0 >> 5, sh = bit0 & 31;
+      unsigned long long win = cocc[w0];
+      if (sh + nb > 32 && w0 + 1 < words) win |= (unsigned long long)cocc[w0 + 1] << 32;
+      const unsigned bits = (unsigned)(win >> sh) & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+      if (bits) {
+        row = ((unsigned long long)bits << RS_PAD) | ((unsigned long long)(bits & 1u) << (RS_PAD - 1));
+        if (own) {
+          atomicMin(&s_box[0], bx); atomicMin(&s_box[1], by); atomicMin(&s_box[2], __ffs(bits) - 1);
+          atomicMax(&s_box[3], bx); atomicMax(&s_box[4], by); atomicMax(&s_box[5], 31 - __clz(bits));
+        }
+      }
     }
+    s_occ[wi] = row;
   }
   __syncthreads();
   const bool any = s_box[3] >= 0;
-  // sample-space box: a sample looks up brick floor(f / 8) (f in [-8, 0) finds the copies of boundary marks)
+  // sample-space box: a sample looks up brick floor(f / 4) (f in [-4, 0) finds the copies of boundary marks)
   float blo[3], bhi[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    blo[d] = s_box[d] == 0 ? -8.01f : 8.0f * s_box[d] - 0.01f;
-    bhi[d] = 8.0f * (s_box[3 + d] + 1) + 0.01f;
+    blo[d] = s_box[d] == 0 ? -(float)RS_BRICK - 0.01f : (float)(RS_BRICK * s_box[d]) - 0.01f;
+    bhi[d] = (float)(RS_BRICK * (s_box[3 + d] + 1)) + 0.01f;
   }
   const float h = 0.5f * (float)(R - 1), stepf = Z > 1 ? 1.0f / (float)(Z - 1) : 0.0f;
   const double step = Z > 1 ? 1.0 / (double)(Z - 1) : 0.0;
@@ -327,16 +338,23 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
   const int j = lane & 7, grp = lane >> 3;
   const int nsteps = (Z + 7) / 8;
   const int ngroups = (S * S + 3) / 4;
-  // 4-ray groups are handed out dynamically (rays that cross the shell cost ~10x the others): one counter per volume
-  for (;;) {
-    int g = 0;
-    if (lane == 0) g = (int)atomicAdd(group_counter + n, 1u);
-    g = __shfl_sync(0xffffffffu, g, 0);
-    if (g >= ngroups) break;
+  // 4-ray groups in a strided order: neighbouring groups (similar cost) go to different warps; the next group's direction
+  // is fetched while the current one is marched
+  const int gstride = gridDim.x * (RS_THREADS / 32);
+  int g = blockIdx.x * (RS_THREADS / 32) + warp;
+  double ndx = 0.0, ndy = 0.0, ndz = 0.0;
+  if (g < ngroups) {
+    const int pc = min(g * 4 + grp, S * S - 1);
+    ndx = __ldg(dirs + pc * 3 + 0); ndy = __ldg(dirs + pc * 3 + 1); ndz = __ldg(dirs + pc * 3 + 2);
+  }
+  for (; g < ngroups; g += gstride) {
+    const double dx = ndx, dy = ndy, dz = ndz;
+    if (g + gstride < ngroups) {
+      const int pc = min((g + gstride) * 4 + grp, S * S - 1);
+      ndx = __ldg(dirs + pc * 3 + 0); ndy = __ldg(dirs + pc * 3 + 1); ndz = __ldg(dirs + pc * 3 + 2);
+    }
     const int pix = g * 4 + grp;
     const bool ray_ok = pix < S * S;
-    const int pixc = ray_ok ? pix : S * S - 1;
-    const double dx = __ldg(dirs + pixc * 3 + 0), dy = __ldg(dirs + pixc * 3 + 1), dz = __ldg(dirs + pixc * 3 + 2);
     const double dx2 = dx * 2.0, dy2 = dy * 2.0, dz2 = dz * 2.0;
     // voxel coordinate of sample k (fp32 estimate): f = h + d*h*2*(1 - k*step) = A - Bk * k
     const float A[3] = {h + 2.0f * (float)dx * h, h + 2.0f * (float)dy * h, h + 2.0f * (float)dz * h};
@@ -367,8 +385,8 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
     int kdone = 0;  // samples [0, kdone) are accounted for
     // phase A: occupancy of every sample of every candidate step, independent iterations (the loads and conversions of
     // several steps are in flight together); windows of 32 steps
-    const float Ab[3] = {A[0] * 0.125f + RS_PAD, A[1] * 0.125f + RS_PAD, A[2] * 0.125f + RS_PAD};
-    const float Bb[3] = {Bk[0] * 0.125f, Bk[1] * 0.125f, Bk[2] * 0.125f};
+    const float Ab[3] = {A[0] * RS_INV_BRICK + RS_PAD, A[1] * RS_INV_BRICK + RS_PAD, A[2] * RS_INV_BRICK + RS_PAD};
+    const float Bb[3] = {Bk[0] * RS_INV_BRICK, Bk[1] * RS_INV_BRICK, Bk[2] * RS_INV_BRICK};
     for (int w0 = s0; w0 < s1; w0 += 32) {   // warp-uniform bounds (ballots inside)
       const int w1 = min(w0 + 32, s1);
       unsigned mine = 0;       // bit i: this lane's sample of step w0 + i is occupied
@@ -379,7 +397,7 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
         const float kf = (float)k;
         const int X = (int)floorf(fmaf(-Bb[0], kf, Ab[0])), Y = (int)floorf(fmaf(-Bb[1], kf, Ab[1])),
                   Zb = (int)floorf(fmaf(-Bb[2], kf, Ab[2]));
-        const bool occupied = ((s_occ[(X & 31) * RS_PB + (Y & 31)] >> (Zb & 31)) & 1u) && k < Z && ray_ok;
+        const bool occupied = ((s_occ[(X & (RS_PB - 1)) * RS_PB + (Y & (RS_PB - 1))] >> (Zb & (RS_PB - 1))) & 1ull) && k < Z && ray_ok;
         mine |= (unsigned)occupied << (s - w0);
         steps_any |= (__ballot_sync(0xffffffffu, occupied) ? 1u : 0u) << (s - w0);
       }
@@ -569,7 +587,7 @@ extern "C" int genre_b200_render_spherical_backward(const float *vox, int64_t N,
 
 extern "C" size_t genre_b200_render_spherical_workspace_bytes(int64_t N, int res) {
   if (N <= 0 || res < 2) return 0;
-  return ((size_t)N * rs_occ_words(res) + (size_t)N) * sizeof(unsigned);   // brick masks + one work counter per volume
+  return (size_t)N * rs_occ_words(res) * sizeof(unsigned);   // one bit per 4^3 brick
 }
 
 // The same renderer with empty-space skipping (see the header of the skipping section): identical results up to ~1e-6.
@@ -606,15 +624,18 @@ extern "C" int genre_b200_render_spherical_forward_skip(const float *vox, int64_
     else render_occupancy_kernel<false><<<og, 256, 0, st>>>(vox, res, v4, (unsigned *)workspace, pre);
   }
   if (int rc = check_launch("render_spherical occupancy kernel")) return rc;
-  unsigned *counters = (unsigned *)workspace + (size_t)N * rs_occ_words(res);
   const int ngroups = (sph_res * sph_res + 3) / 4;
-  const int ctas = ngroups < RS_CTAS_PER_VOLUME * (RS_THREADS / 32) ? (ngroups + RS_THREADS / 32 - 1) / (RS_THREADS / 32) : RS_CTAS_PER_VOLUME;
+  // one wave of resident CTAs over the whole batch (4 per SM at 64 registers; 148 SMs), warps stride over the ray groups
+  int ctas = (int)((148 * 4) / N);
+  const int max_ctas = (ngroups + RS_THREADS / 32 - 1) / (RS_THREADS / 32);
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
   dim3 rg((unsigned)ctas, (unsigned)N);
   if (use_pre)
     render_spherical_forward_skip_kernel<true><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                          (const unsigned *)workspace, counters, out, pre);
+                                                                          (const unsigned *)workspace, out, pre);
   else
     render_spherical_forward_skip_kernel<false><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                           (const unsigned *)workspace, counters, out, pre);
+                                                                           (const unsigned *)workspace, out, pre);
   return check_launch("render_spherical forward kernel (empty-space skipping)");
 }

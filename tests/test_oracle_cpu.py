@@ -261,21 +261,21 @@ def test_config1_depth_to_voxel_to_spherical_on_one_map(oracle):
 
 def test_render_skip_brick_rule_never_hides_an_occupied_tap():
     """The empty-space-skipping renderer (csrc/render_sph.cu) may only call a sample empty when none of its VALID trilinear taps
-    is occupied.  Emulates its marking rule (occupied voxel v marks bricks floor((v-2)/8) .. floor((v+1)/8), clipped to the
-    volume; a marked boundary brick 0 also marks the outside brick -1) and its lookup (brick floor(f_est / 8), f_est an fp32
+    is occupied.  Emulates its marking rule (occupied voxel v marks bricks floor((v-2)/4) .. floor((v+1)/4), clipped to the
+    volume; a marked boundary brick 0 also marks the outside brick -1) and its lookup (brick floor(f_est / 4), f_est an fp32
     estimate within 1e-4 of the exact coordinate f) in one dimension -- the 3-D rule is the product of three such tests --
     over every voxel position and a dense sweep of sample coordinates, boundary cases included."""
-    R = 128
+    R, BR = 128, 4
     rng = np.random.RandomState(0)
     for v in list(range(0, 20)) + list(range(100, 128)) + [63, 64, 65]:
-        marked = set(range(max(v - 2, 0) // 8, min(v + 1, R - 1) // 8 + 1))
+        marked = set(range(max(v - 2, 0) // BR, min(v + 1, R - 1) // BR + 1))
         if 0 in marked:
             marked.add(-1)
         f = np.concatenate([np.linspace(-2.0, 130.0, 26401), v + rng.uniform(-1.2, 1.2, 2000)])
         t0 = np.floor(f).astype(int)
         touches = ((t0 == v) & (t0 >= 0) & (t0 < R)) | ((t0 + 1 == v) & (t0 + 1 >= 0) & (t0 + 1 < R))
         for err in (-1e-4, 0.0, 1e-4):
-            brick = np.floor((f + err) / 8.0).astype(int)
+            brick = np.floor((f + err) / BR).astype(int)
             hidden = touches & ~np.isin(brick, list(marked))
             # a tap may only be "hidden" when its interpolation weight is below the estimate's error
             w = np.where(t0 == v, 1.0 - (f - t0), f - t0)
