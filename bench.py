@@ -395,7 +395,7 @@ def run_b200(args):
     roofline = None
     if rank == 0 and "roofline" not in skip:
         try:
-            roofline = roofline_leg(torch, net, dev, B)
+            roofline = roofline_leg(torch, net, dev, B, inputs[0])
         except Exception as e:
             roofline = {"error": repr(e)[:300]}
 
@@ -513,16 +513,24 @@ def e2e_leg(torch, net, dev, B, K, rank, world, barrier, max_over_ranks, use_gra
             "pipeline": "2 slots x 3 streams (H2D | Net.forward%s | D2H)" % (" as a CUDA graph" if slots[0]["run"] is not None else "")}
 
 
-def roofline_leg(torch, net, dev, B):
-    """Each hot-path op of the step, alone, at the step's batch: CUDA events around a CUDA-graph replay of the public call
-    (so that launch gaps are not billed to the kernels), algorithmic bytes / flops from SURVEY 8(d)."""
-    from genre_shapehd_b200 import _lib
-    from genre_shapehd_b200.synth import bench_depth_batch
+def roofline_leg(torch, net, dev, B, x):
+    """Each hot-path op of the step, alone, at the step's batch and ON THE STEP'S OWN TENSORS (one real forward is run first and
+    its intermediates captured): CUDA events around a CUDA-graph replay of the public call (so that launch gaps are not billed
+    to the kernels), algorithmic bytes / flops from SURVEY 8(d)."""
+    from genre_shapehd_b200 import _lib, ops_conv
     from toolbox.cam_bp.cam_bp.functions import SphericalBackProjection
     from toolbox.spherical_proj import gen_sph_grid
     hbm, tens, src = measured_peaks()
-    depth = torch.from_numpy(bench_depth_batch(B)).to(dev)
     layer = net.proj_depth
+    cap = {}
+    h1 = net.depth_and_inpaint.proj_depth.register_forward_pre_hook(lambda m, a: cap.__setitem__("depth", a[0].detach().clone()))
+    h2 = net.depth_and_inpaint.render_spherical.register_forward_pre_hook(lambda m, a: cap.__setitem__("vox", a[0].detach().clone()))
+    h3 = net.refine_net.register_forward_pre_hook(lambda m, a: cap.__setitem__("refine_in", a[0].detach().clone()))
+    with torch.no_grad():
+        out = net(x)
+    for h in (h1, h2, h3):
+        h.remove()
+    depth, vox, refine_in = cap["depth"], cap["vox"], cap["refine_in"]     # depth: the permuted + flipped view the caller passes
     reps = 30
     with torch.no_grad():
         # cam_bp whole op (memset node + project + splat)
@@ -539,23 +547,20 @@ def roofline_leg(torch, net, dev, B):
                   cd.data_ptr(), *cd.stride(), RES, ws.data_ptr(), nbytes, st)
         ms_splat = time_cuda(torch, lambda: _lib.call("genre_b200_voxelize_stage_splat", B, H * W, RES, tdf.data_ptr(), None, 1.0,
                                                       -1.0 / 16777216.0, 0.0, ws.data_ptr(), nbytes, st), reps)
-        # render_spherical on the clamped projection (as depth_pred_with_sph_inpaint.py:124 calls it)
+        # render_spherical on the volume the caller hands it: clamp(proj * 50, 1e-5, 1 - 1e-5) (depth_pred_with_sph_inpaint.py:124)
         rend = net.depth_and_inpaint.render_spherical
-        vox = torch.clamp(proj * 50, 1e-5, 1 - 1e-5)
         run, sph = graph_of(torch, lambda: rend(vox))
         ms_rend = time_cuda(torch, run, reps)
         rend_bytes = B * (4 * RES ** 3 + 4 * 128 * 128)
-        # spherical back-projection (tdf + cnt out)
+        # spherical back-projection (tdf + cnt out) of the inpainted map (genre_full_model.py:134-143)
         grid = gen_sph_grid().to(dev).expand(B, -1, -1, -1, -1)
-        sph_in = (1 - sph).contiguous()
+        sph_in = (1 - out["pred_sph_full"][:, :, 16:144, 16:144]).contiguous()
         run, _ = graph_of(torch, lambda: SphericalBackProjection.apply(sph_in, grid, RES))
         ms_sbp = time_cuda(torch, run, reps)
         sbp_bytes = B * (4 * 128 * 128 + 8 * RES ** 3)
-        # the refiner
-        x = torch.rand(B, 2, RES, RES, RES, device=dev)
-        run, _ = graph_of(torch, lambda: net.refine_net(x))
+        # the refiner on its real input
+        run, _ = graph_of(torch, lambda: net.refine_net(refine_in))
         ms_unet = time_cuda(torch, run, 10)
-    from genre_shapehd_b200 import ops_conv
     tf_useful = UNET3D_GFLOP * 1e9 * B / (ms_unet * 1e-3) / 1e12
     ncu = None
     f = os.path.join(REPO, "profiles", "r02_tensor_pipe.json")
@@ -572,7 +577,8 @@ def roofline_leg(torch, net, dev, B):
         except Exception:
             pass
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "cam_bp whole op: cam_project_kernel + vox_splat_kernel (+ counter memset), batch %d" % B,
+    occ_frac = float((vox > 1e-5).float().mean())
+    return {"bound": "hbm", "kernel": "cam_bp whole op: cam_project_kernel + vox_splat_kernel (+ counter memset), batch %d, the step's own depth maps" % B,
             "achieved": gbs(cam_bytes, ms_cam), "peak": hbm, "unit": "GB/s", "frac": gbs(cam_bytes, ms_cam) / hbm,
             "traffic": (traffic or {}).get("dram_bytes_per_launch_b16"), "traffic_source": "ncu --set full capture, profiles/splat_traffic.json (static: needs a profiler)",
             "peak_source": src, "algorithmic_bytes_per_launch": cam_bytes, "op_us": ms_cam * 1e3,
@@ -580,7 +586,8 @@ def roofline_leg(torch, net, dev, B):
                 "vox_splat_kernel": {"bound": "hbm", "us": ms_splat * 1e3, "achieved": gbs(cam_bytes, ms_splat), "frac": gbs(cam_bytes, ms_splat) / hbm,
                                      "algorithmic_bytes": cam_bytes},
                 "render_spherical": {"bound": "hbm", "us": ms_rend * 1e3, "achieved": gbs(rend_bytes, ms_rend), "frac": gbs(rend_bytes, ms_rend) / hbm,
-                                     "algorithmic_bytes": rend_bytes},
+                                     "algorithmic_bytes": rend_bytes, "kernels": "render_occupancy128_kernel + render_spherical_forward_skip_kernel",
+                                     "occupied_voxel_fraction_of_the_input": occ_frac},
                 "spherical_back_projection": {"bound": "hbm", "us": ms_sbp * 1e3, "achieved": gbs(sbp_bytes, ms_sbp), "frac": gbs(sbp_bytes, ms_sbp) / hbm,
                                               "algorithmic_bytes": sbp_bytes},
                 "unet3d_refiner": {"bound": "tensor", "ms": ms_unet, "achieved": tf_useful, "peak": tens, "unit": "TFLOP/s (useful: 78.0 GFLOP/shape)",

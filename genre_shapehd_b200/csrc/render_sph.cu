@@ -13,6 +13,7 @@
 // shuffle product-scan and crosses 32-sample chunks through a register carry.  Only the [N,S,S] map
 // is written.  Sample positions are formed in fp64 from the fp64 direction table exactly like the
 // numpy code, then rounded to fp32, so they equal the reference's registered `grid` buffer.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gb {
@@ -268,18 +269,20 @@ render_occupancy128_kernel(const float *__restrict__ vox, unsigned *__restrict__
   }
 }
 
-template <bool PRE>
-__global__ void __launch_bounds__(RS_THREADS)
+// OCC: resident CTAs per SM the register allocation is bounded for (5: 48 registers with 64 B of spills; 4: 64, none)
+template <bool PRE, int OCC>
+__global__ void __launch_bounds__(RS_THREADS, OCC)
 render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const double *__restrict__ dirs, int S, int Z,
                                      const float *__restrict__ depth_weight, const unsigned *__restrict__ occ,
                                      float *__restrict__ out, const VoxPre pre) {
   __shared__ unsigned long long s_occ[RS_PB * RS_PB];  // padded brick mask: word = X * 64 + Y, bit = Z (padded brick coordinates)
   __shared__ float s_S[RS_MAX_Z + 1];                  // S[k] = sum_{j<k} q^j w_j
-  __shared__ int s_box[6];                             // marked-brick bounding box: min x,y,z, max x,y,z (unpadded)
+  __shared__ int s_box[7];                             // marked-brick bounding box: min x,y,z, max x,y,z (unpadded); [6] = marked bricks
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = rs_bricks(R), words = rs_occ_words(R);
   if (tid < 3) s_box[tid] = nb;
   else if (tid < 6) s_box[tid] = -1;
+  else if (tid == 6) s_box[6] = 0;
   // prefix table of q^j w_j: warp 0, 32 entries per pass
   if (warp == 0) {
     float run = 0.0f;
@@ -318,6 +321,7 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
         if (own) {
           atomicMin(&s_box[0], bx); atomicMin(&s_box[1], by); atomicMin(&s_box[2], __ffs(bits) - 1);
           atomicMax(&s_box[3], bx); atomicMax(&s_box[4], by); atomicMax(&s_box[5], 31 - __clz(bits));
+          atomicAdd(&s_box[6], __popc(bits));
         }
       }
     }
@@ -325,6 +329,9 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
   }
   __syncthreads();
   const bool any = s_box[3] >= 0;
+  // a volume with occupied voxels in most bricks (nothing to skip) takes every step of the box range on the exact path
+  // without the per-sample tests
+  const bool dense = s_box[6] * 5 > nb * nb * nb * 2;
   // sample-space box: a sample looks up brick floor(f / 4) (f in [-4, 0) finds the copies of boundary marks)
   float blo[3], bhi[3];
 #pragma unroll
@@ -391,6 +398,10 @@ render_spherical_forward_skip_kernel(const float *__restrict__ vox, int R, const
       const int w1 = min(w0 + 32, s1);
       unsigned mine = 0;       // bit i: this lane's sample of step w0 + i is occupied
       unsigned steps_any = 0;  // bit i: some lane's sample of step w0 + i is occupied (warp-uniform)
+      if (dense) {
+        steps_any = w1 - w0 == 32 ? 0xffffffffu : (1u << (w1 - w0)) - 1u;
+        mine = ray_ok ? steps_any : 0u;
+      } else
 #pragma unroll 4
       for (int s = w0; s < w1; ++s) {
         const int k = 8 * s + j;
@@ -625,17 +636,25 @@ extern "C" int genre_b200_render_spherical_forward_skip(const float *vox, int64_
   }
   if (int rc = check_launch("render_spherical occupancy kernel")) return rc;
   const int ngroups = (sph_res * sph_res + 3) / 4;
-  // one wave of resident CTAs over the whole batch (4 per SM at 64 registers; 148 SMs), warps stride over the ray groups
-  int ctas = (int)((148 * 4) / N);
+  // one wave of resident CTAs over the whole batch (OCC per SM, 148 SMs), warps stride over the ray groups
+  static int occ = 0;
+  if (!occ) {
+    const char *e = getenv("GENRE_B200_RENDER_OCC");   // tuning knob (profiles/): 4 or 5
+    occ = (e && atoi(e) == 4) ? 4 : 5;
+  }
+  int ctas = (int)((148 * occ) / N);
   const int max_ctas = (ngroups + RS_THREADS / 32 - 1) / (RS_THREADS / 32);
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   dim3 rg((unsigned)ctas, (unsigned)N);
-  if (use_pre)
-    render_spherical_forward_skip_kernel<true><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                          (const unsigned *)workspace, out, pre);
-  else
-    render_spherical_forward_skip_kernel<false><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight,
-                                                                           (const unsigned *)workspace, out, pre);
+#define GB_RS_LAUNCH(PRE_, OCC_)                                                                                              \
+  render_spherical_forward_skip_kernel<PRE_, OCC_><<<rg, RS_THREADS, 0, st>>>(vox, res, dirs, sph_res, z_res, depth_weight, \
+                                                                              (const unsigned *)workspace, out, pre)
+  if (use_pre) {
+    if (occ == 4) GB_RS_LAUNCH(true, 4); else GB_RS_LAUNCH(true, 5);
+  } else {
+    if (occ == 4) GB_RS_LAUNCH(false, 4); else GB_RS_LAUNCH(false, 5);
+  }
+#undef GB_RS_LAUNCH
   return check_launch("render_spherical forward kernel (empty-space skipping)");
 }
