@@ -4,7 +4,7 @@
 A plain random init makes net1's min/max head predict ~(0, 0): every pixel then unprojects 2.2 units in front of the
 grid, cam_bp hits nothing and the 3D path runs on an empty volume.  There are no checkpoints offline, so the head's
 last bias is set to the dataset's depth range and the depth decoder's last layer is scaled up so that the relative
-depth varies over the silhouette.  Everything else keeps PyTorch's default initialisation.
+depth varies over the silhouette (gain 10: a surface with ~2 voxels of relief; a trained net1 predicts smooth surfaces).  Everything else keeps PyTorch's default initialisation.
 """
 import types
 
@@ -18,7 +18,7 @@ def genre_opt(joint_train=False):
                               net1_path=None, load_offline=False)
 
 
-def init_genre_net_for_bench(net, depth_range=(1.85, 2.55), depth_gain=40.0):
+def init_genre_net_for_bench(net, depth_range=(1.85, 2.55), depth_gain=10.0):
     """net: models.genre_full_model.Net (reference class, unmodified).  In-place; returns net."""
     net1 = net.depth_and_inpaint.net1
     with torch.no_grad():

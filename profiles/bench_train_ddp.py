@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""BASELINE configs[3] (ShapeHD fine-tune step and 3D-WGAN-GP critic step, batch 8 per GPU, DDP over NCCL) on the
+"""BASELINE configs[3] and [4] (ShapeHD fine-tune step and 3D-WGAN-GP critic step, batch 8 per GPU; GenRe end-to-end fine-tune
+with the Chamfer op, batch 4 per GPU; DDP over NCCL) on the
 networks drop-in, driven through the reference's FROZEN classes (baseline/_ref):
   shapehd step : models/shapehd.py Net (:82-118: two marrnet2 = ImageEncoder -> VoxelDecoder, frozen D) + the loss of
                  :67-79 (BCE-with-logits + w * -mean(D(sigmoid(voxel)))) + Adam on marrnet2 (:42-47)
@@ -27,7 +28,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 
-def run(dev, world, rank, local, batch=8, steps=6, warmup=3, which=("shapehd", "wgan")):
+def run(dev, world, rank, local, batch=8, steps=6, warmup=3, which=("shapehd", "wgan", "genre"), genre_batch=4):
     from genre_shapehd_b200 import compat, dist_util, ops_conv
     compat.bootstrap()
     import models.shapehd as shd
@@ -126,6 +127,51 @@ def run(dev, world, rank, local, batch=8, steps=6, warmup=3, which=("shapehd", "
             res["wgangp_critic"].update({"step_ms_no_sync": ms_ns, "exposed_allreduce_ms": max(0.0, ms - ms_ns),
                                          "exposed_allreduce_frac": max(0.0, ms - ms_ns) / ms,
                                          "allreduce_bytes": 4 * sum(p.numel() for p in Dn.parameters())})
+    # ---- GenRe end-to-end fine-tune step + Chamfer (BASELINE configs[4], batch 4 per GPU) ---------------------------------
+    if "genre" in which:
+        import models.genre_full_model as gfm
+        from genre_shapehd_b200.synth_genre import genre_inputs, genre_opt, init_genre_net_for_bench
+        from nndistance.functions.nnd import nndistance
+        Bg = genre_batch
+        gnet = gfm.Net(genre_opt(joint_train=True), gfm.Model)       # frozen class; joint_train: gradients reach net1 / net2
+        init_genre_net_for_bench(gnet)                                # through cam_bp / render_spherical / spherical bp backward
+        gnet = gnet.to(dev).train()
+        gddp = wrap(gnet)
+        gopt = torch.optim.Adam(gnet.parameters(), lr=1e-4)
+        gin = genre_inputs(Bg, dev, seed=5 + rank)
+        gvox = (torch.rand(Bg, 1, 128, 128, 128, device=dev) < 0.05).float()
+        npts = 4096
+        gen = torch.Generator(dev).manual_seed(3 + rank)
+        xyz2 = torch.rand(Bg, npts, 3, device=dev, generator=gen) - 0.5
+        xyz1 = (torch.rand(Bg, npts, 3, device=dev, generator=gen) - 0.5).requires_grad_(True)
+
+        def genre_step(sync=True):
+            gopt.zero_grad(set_to_none=True)
+            xyz1.grad = None
+            ctx = contextlib.nullcontext() if (sync or world == 1) else gddp.no_sync()
+            with ctx:
+                pred = gddp(types.SimpleNamespace(rgb=gin.rgb, silhou=gin.silhou))
+                voxel_loss = F.binary_cross_entropy_with_logits(pred["pred_voxel"], gvox)           # genre_full_model.py:64
+                surface_loss = F.binary_cross_entropy(torch.sigmoid(pred["pred_voxel"]) * gvox, gvox)  # :65-66
+                d1, d2 = nndistance(xyz1, xyz2)                        # the shipped-but-unwired Chamfer op, timed in the step
+                # the reference's joint loss also supervises net1's normal / silhouette heads (marrnet1.py:120-136): keep them in
+                # the graph (weight 0) so that every parameter receives a gradient, as DDP's reducer expects
+                loss = voxel_loss + surface_loss + (d1.mean() + d2.mean()) + 0.0 * (pred["normal"].mean() + pred["silhou"].mean())
+                loss.backward()
+            gopt.step()
+            return loss.detach()
+        if os.environ.get("NCU") == "genre":
+            return _ncu(genre_step)
+        ms, loss = timed(genre_step)
+        res["genre_finetune"] = {"batch_per_gpu": Bg, "step_ms": ms, "shapes_per_s": world * Bg / ms * 1e3, "loss_finite": bool(loss == loss),
+                                 "chamfer_points": npts,
+                                 "workload": "BASELINE configs[4]: frozen genre_full_model.Net, joint_train, voxel + surface loss, "
+                                             "backward through every toolbox op, + nndistance fwd/bwd on [B,4096,3] clouds"}
+        if world > 1:
+            ms_ns, _ = timed(lambda: genre_step(sync=False))
+            res["genre_finetune"].update({"step_ms_no_sync": ms_ns, "exposed_allreduce_ms": max(0.0, ms - ms_ns),
+                                          "exposed_allreduce_frac": max(0.0, ms - ms_ns) / ms,
+                                          "allreduce_bytes": 4 * sum(p.numel() for p in gnet.parameters() if p.requires_grad)})
     return res
 
 
@@ -148,7 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--which", default="shapehd,wgan")
+    ap.add_argument("--which", default="shapehd,wgan,genre")
     args = ap.parse_args()
     world, rank, local = dist_util.env_world()
     torch.cuda.set_device(local)
