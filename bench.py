@@ -425,7 +425,13 @@ def run_b200(args):
         try:
             sys.path.insert(0, os.path.join(REPO, "profiles"))
             import bench_train_ddp
-            ddp = bench_train_ddp.run(dev, world, rank, local, batch=8, steps=6, warmup=3)
+            ddp = {}
+            for which in ("shapehd", "wgan", "genre"):      # one at a time: a failing workload must not hide the others
+                try:
+                    ddp.update(bench_train_ddp.run(dev, world, rank, local, batch=8, steps=6, warmup=3, which=(which,)))
+                except Exception as e:
+                    ddp[which + "_error"] = repr(e)[:300]
+                torch.cuda.empty_cache()
         except Exception as e:
             ddp = {"error": repr(e)[:300]}
 

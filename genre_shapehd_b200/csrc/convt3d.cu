@@ -20,6 +20,9 @@
 // MT x NPAD fp32 columns in TMEM.  Warps 0-3: halo producers (cp.async 16 B, zero-fill = padding), then epilogue
 // (tcgen05.ld -> scale/shift/LeakyReLU -> blocked store).  Warp 4: TMEM allocation + single-thread MMA issue.
 // Pipeline: STAGES-deep ring of (halo chunk, weight chunk) with full/empty mbarriers; tcgen05.commit frees a slot.
+#include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype (the entry point is resolved through the runtime: no -lcuda)
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 
 namespace gb {
@@ -86,6 +89,13 @@ __device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t 
                    smem_u32(sdst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one halo box: coordinates (16-byte lane 0, x, y, channel group, plane); out-of-range x / y read as zeros
+__device__ __forceinline__ void tma_load_5d(void *sdst, const CUtensorMap *tmap, int x, int y, int cg, int plane, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(sdst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(x), "r"(y), "r"(cg), "r"(plane), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -176,14 +186,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 // so the hi*hi products and the 2^11-scaled cross terms keep separate accumulators (the tensor core's fp32 accumulator
 // truncates: a step's error scales with the partial sum it joins, and the cross terms would otherwise ride on the big one),
 // and the epilogue returns acc_hi + 2^-11 * acc_cross.  2 MMAs per K step instead of the 3 of a K-expanded split.
-template <int T, int NPAD, int MT, bool X2 = false>
+// TMA: the halo of a channel group arrives as ONE cp.async.bulk.tensor (5-D tiled tensor map over [plane][cg][H][W][16 B], box
+// [1][1][PY][PX][16 B], out-of-bounds elements zero-filled = the convolution's padding) instead of PY*PX 16-byte cp.async
+// issued by 128 threads; each channel group then starts on a 128-byte boundary of shared memory (the LBO of the A descriptor
+// is that padded stride).
+template <int T, int NPAD, int MT, bool X2 = false, bool TMA = false>
 struct ConvTCfg {
   static constexpr int W = 8 * MT;
   static constexpr int PY = CT_BY + T - 1, PX = W + T - 1;     // halo extent
   static constexpr int PARTS = X2 ? 2 : 1;
   static constexpr int NACC = PARTS * NPAD;                    // accumulator columns per M-tile = width of the B operand
-  static constexpr int A_CG_BYTES = PY * PX * 16;              // one channel group of the halo = LBO of A
-  static constexpr int A_BYTES = PARTS * CT_KCG * A_CG_BYTES;  // [part][channel group][halo]
+  static constexpr int A_CG_BYTES = PY * PX * 16;              // one channel group of the halo
+  static constexpr int A_CG_STRIDE = TMA ? ((A_CG_BYTES + 127) / 128) * 128 : A_CG_BYTES;   // its pitch in shared memory = LBO of A
+  static constexpr int A_BYTES = PARTS * CT_KCG * A_CG_STRIDE; // [part][channel group][halo]
+  static constexpr int A_TX_BYTES = PARTS * CT_KCG * A_CG_BYTES;  // bytes the tensor copies of one stage deliver
   static constexpr int B_TAP_BYTES = 2 * (NACC / 8) * 128;     // one (y,x) tap: [2 kcore][NACC/8][8 rows][16 B]
   // A stage holds the halo of one (z tap, K chunk) and the weights of ROWS of its T tap rows; YS = T / ROWS (rounded up)
   // stages walk the same halo when all T*T taps do not fit twice into shared memory (X2 with 5x5 union taps: 128 KB).
@@ -228,11 +244,11 @@ struct ConvTCfg {
 //         N = 16 columns of which 8 are the output classes; the epilogue adds the bias (shift[0]), optionally applies
 //         the sigmoid, and writes the NCDHW fp32 volume directly.
 // OP: operand type: 0 = TF32 (fp32 storage), 1 = fp16, 2 = fp16 hi/lo split (X2, see ConvTCfg)
-template <int TZ, int T, int NPAD, int MT, int MODE, int OP>
+template <int TZ, int T, int NPAD, int MT, int MODE, int OP, bool TMA>
 __global__ void __launch_bounds__(CT_THREADS, 1)
-convt3d_s2_kernel(const ConvTParams p) {
+convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1) {
   constexpr bool F16 = OP != 0, X2 = OP == 2;
-  using Cfg = ConvTCfg<T, NPAD, MT, X2>;
+  using Cfg = ConvTCfg<T, NPAD, MT, X2, TMA>;
   constexpr int NACC = Cfg::NACC;
   constexpr float LO_SCALE = 1.0f / 2048.0f;   // the cross-term accumulators hold 2^11 x their value
   constexpr bool PAR = MODE == 0, MERGE = MODE == 2, MERGE8 = MODE == 3, C1 = MODE == 4;
@@ -280,7 +296,8 @@ convt3d_s2_kernel(const ConvTParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full[s], CT_PRODUCERS + 1);  // 128 producer arrivals + the expect_tx arrival of the weight copy
+      mbar_init(&full[s], TMA ? 1 : CT_PRODUCERS + 1);  // cp.async path: 128 producer arrivals + the expect_tx arrival of the
+                                                        // weight copy; TMA path: the one expect_tx arrival (halo + weight bytes)
       mbar_init(&empty[s], 1);                // one tcgen05.commit
     }
     mbar_init(accum_full, 1);
@@ -298,6 +315,38 @@ convt3d_s2_kernel(const ConvTParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
+    if constexpr (TMA) {
+      // ===================== producer: ONE thread issues the tensor copies of every stage ==========================
+      if (tid == 0) {
+        int it = 0;
+        for (int q = 0; q < n_q; ++q) {
+          int tz, kc, ys, bz, by, bx;
+          if (!stage_of(q, tz, kc, ys, bz, by, bx)) continue;
+          const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
+          ++it;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
+          const int rows = (ys + 1) * Cfg::ROWS <= T ? Cfg::ROWS : T - ys * Cfg::ROWS;
+          const uint32_t wbytes = (uint32_t)(rows * T * Cfg::B_TAP_BYTES);
+          const float *wsrc = p.wpack + ((((size_t)par * TZ + tz) * nchunk + kc) * (size_t)(T * T * Cfg::B_TAP_BYTES / 4)) +
+                              (size_t)ys * Cfg::ROWS * T * (Cfg::B_TAP_BYTES / 4);
+          mbar_arrive_expect_tx(&full[s], wbytes + (uint32_t)Cfg::A_TX_BYTES);
+          bulk_g2s(sa + Cfg::A_BYTES, wsrc, wbytes, &full[s]);
+          const int zi = zj + bz - tz;
+          const int gy0 = y0 + by - (T - 1), gx0 = x0 + bx - (T - 1);
+#pragma unroll
+          for (int part = 0; part < Cfg::PARTS; ++part) {
+#pragma unroll
+            for (int c = 0; c < CT_KCG; ++c) {
+              int cg = kc * CT_KCG + c;
+              const CUtensorMap *tm = &tmap0;
+              if (cg >= p.cg0) { cg -= p.cg0; tm = &tmap1; }
+              tma_load_5d(sa + (part * CT_KCG + c) * Cfg::A_CG_STRIDE, tm, gx0, gy0, cg, (b * p.D + zi) * Cfg::PARTS + part, &full[s]);
+            }
+          }
+        }
+      }
+    } else {
     // ===================== producers: halo (cp.async, zero-fill) + weights (one bulk copy per stage) ==========
     // this thread's halo positions are the same for every stage: precompute (offset in the cg plane, halo row/col)
     int hoff[Cfg::POS_PER_THREAD], hy[Cfg::POS_PER_THREAD], hx[Cfg::POS_PER_THREAD];
@@ -352,7 +401,7 @@ convt3d_s2_kernel(const ConvTParams p) {
             const int gy = gy0 + hy[i], gx = gx0 + hx[i];
             const bool ok = (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
             const float *g = ok ? plane + ((size_t)gy * p.W + gx) * 4 : plane;
-            cp_async16_zfill(sa + (part * CT_KCG + c) * Cfg::A_CG_BYTES + hoff[i], g, ok);
+            cp_async16_zfill(sa + (part * CT_KCG + c) * Cfg::A_CG_STRIDE + hoff[i], g, ok);
           }
         }
       }
@@ -360,6 +409,7 @@ convt3d_s2_kernel(const ConvTParams p) {
     }
     for (int e = 0; e < LAG; ++e) publish();  // drain: empty groups push the last real ones through
 
+    }
     // ===================== epilogue: TMEM -> registers -> act(acc*scale+shift) -> blocked global store =========
     mbar_wait(accum_full, 0);
     tc_fence_after();
@@ -497,12 +547,12 @@ convt3d_s2_kernel(const ConvTParams p) {
           for (int mt = 0; mt < MT; ++mt) {
             // rows of this M-tile under tap (ty,tx): halo row (T-1-ty) + y, column (T-1-tx) + 8*mt + x
             const uint32_t a0 = sa + (((T - 1 - ty) * Cfg::PX) + (T - 1 - tx) + 8 * mt) * 16;
-            const uint64_t adesc = umma_desc(a0, Cfg::A_CG_BYTES, Cfg::PX * 16);
+            const uint64_t adesc = umma_desc(a0, Cfg::A_CG_STRIDE, Cfg::PX * 16);
             const bool acc = !first || (r | tx);
             if (F16) umma_f16(tmem_base + mt * NACC, adesc, bdesc, idesc, acc);
             else umma_tf32(tmem_base + mt * NACC, adesc, bdesc, idesc, acc);
             if constexpr (X2) {
-              const uint64_t adesc_lo = umma_desc(a0 + CT_KCG * Cfg::A_CG_BYTES, Cfg::A_CG_BYTES, Cfg::PX * 16);
+              const uint64_t adesc_lo = umma_desc(a0 + CT_KCG * Cfg::A_CG_STRIDE, Cfg::A_CG_STRIDE, Cfg::PX * 16);
               umma_f16(tmem_base + mt * NACC + NPAD, adesc_lo, bdesc, idesc_lo, true);
             }
           }
@@ -520,10 +570,49 @@ convt3d_s2_kernel(const ConvTParams p) {
   }
 }
 
-template <int TZ, int T, int NPAD, int MT, int MODE, int OP>
-static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
-  using Cfg = ConvTCfg<T, NPAD, MT, OP == 2>;
-  auto kern = convt3d_s2_kernel<TZ, T, NPAD, MT, MODE, OP>;
+// ---- tensor maps of the activation operands (host) ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tmap_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+// blocked activations [planes][ncg][H][W][16 B] as a 5-D map of 4-byte elements (4, W, H, ncg, planes); box = one channel
+// group's halo (4, PX, PY, 1, 1); elements outside [0,W) x [0,H) are delivered as zeros
+static bool make_halo_tmap(CUtensorMap *m, const void *base, long long planes, int ncg, int H, int W, int PX, int PY) {
+  EncodeTiledFn enc = tmap_encoder();
+  if (!enc || !base || ncg <= 0) return false;
+  const cuuint64_t gdim[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)ncg, (cuuint64_t)planes};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)ncg * H * W * 16};
+  const cuuint32_t box[5] = {4, (cuuint32_t)PX, (cuuint32_t)PY, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// GENRE_B200_CONV_TMA=0 keeps the cp.async halo producer
+static bool conv_use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("GENRE_B200_CONV_TMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && tmap_encoder() != nullptr;
+}
+
+template <int TZ, int T, int NPAD, int MT, int MODE, int OP, bool TMA>
+static int launch_convt_variant(const ConvTParams &p, cudaStream_t st) {
+  using Cfg = ConvTCfg<T, NPAD, MT, OP == 2, TMA>;
+  auto kern = convt3d_s2_kernel<TZ, T, NPAD, MT, MODE, OP, TMA>;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -538,9 +627,25 @@ static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
   ConvTParams q = p;
   q.xtiles = p.W / Cfg::W;
   if (q.xtiles < 1 || q.xtiles * Cfg::W != p.W) return fail_arg(GENRE_B200_EINVAL, "convt3d: W=%d is not a multiple of the %d-wide tile", p.W, Cfg::W);
+  CUtensorMap tm0, tm1;
+  memset(&tm0, 0, sizeof(tm0));
+  memset(&tm1, 0, sizeof(tm1));
+  if (TMA) {
+    const long long planes = (long long)p.B * p.D * Cfg::PARTS;
+    if (!make_halo_tmap(&tm0, p.src0, planes, p.cg0, p.H, p.W, Cfg::PX, Cfg::PY))
+      return fail_arg(GENRE_B200_EINVAL, "convt3d: cuTensorMapEncodeTiled failed for the first operand");
+    if (p.cg1 > 0 && !make_halo_tmap(&tm1, p.src1, planes, p.cg1, p.H, p.W, Cfg::PX, Cfg::PY))
+      return fail_arg(GENRE_B200_EINVAL, "convt3d: cuTensorMapEncodeTiled failed for the second operand");
+  }
   dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY) * q.xtiles), MODE == 0 ? 8 : MODE == 2 ? 2 : 1);
-  kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(q);
+  kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(q, tm0, tm1);
   return check_launch("convt3d_s2 kernel");
+}
+
+template <int TZ, int T, int NPAD, int MT, int MODE, int OP>
+static int launch_convt_impl(const ConvTParams &p, cudaStream_t st) {
+  if (conv_use_tma()) return launch_convt_variant<TZ, T, NPAD, MT, MODE, OP, true>(p, st);
+  return launch_convt_variant<TZ, T, NPAD, MT, MODE, OP, false>(p, st);
 }
 
 static thread_local int g_conv_op = 0;  // operand type of the next launch (set by the C ABI entry points): 0 TF32, 1 fp16, 2 fp16 hi/lo

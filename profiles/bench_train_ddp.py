@@ -154,9 +154,11 @@ def run(dev, world, rank, local, batch=8, steps=6, warmup=3, which=("shapehd", "
                 voxel_loss = F.binary_cross_entropy_with_logits(pred["pred_voxel"], gvox)           # genre_full_model.py:64
                 surface_loss = F.binary_cross_entropy(torch.sigmoid(pred["pred_voxel"]) * gvox, gvox)  # :65-66
                 d1, d2 = nndistance(xyz1, xyz2)                        # the shipped-but-unwired Chamfer op, timed in the step
-                # the reference's joint loss also supervises net1's normal / silhouette heads (marrnet1.py:120-136): keep them in
+                # the reference's joint loss also supervises net1's normal / silhouette / min-max heads (marrnet1.py:120-136; the 3D path
+                # reads depth_minmax detached, depth_pred_with_sph_inpaint.py:135): keep them in
                 # the graph (weight 0) so that every parameter receives a gradient, as DDP's reducer expects
-                loss = voxel_loss + surface_loss + (d1.mean() + d2.mean()) + 0.0 * (pred["normal"].mean() + pred["silhou"].mean())
+                loss = voxel_loss + surface_loss + (d1.mean() + d2.mean()) + 0.0 * (pred["normal"].mean() + pred["silhou"].mean() +
+                                                                                    pred["depth_minmax"].mean())
                 loss.backward()
             gopt.step()
             return loss.detach()
