@@ -995,6 +995,12 @@ def _operand_of(x):
     PRECISION, reusing the fp32 blocked twin a previous custom layer left behind; (operand, padded channels) or None"""
     c = x.shape[1]
     twin = _cached_blocked(x)
+    if _x2():       # fp16 hi/lo parts of the (zero-padded) fp32 blocked tensor
+        if twin is None:
+            if c % 4 != 0 or isinstance(x, BlockedActivation):
+                return None
+            twin = to_blocked(x, 4)
+        return _split2(twin), ((twin.shape[1] + 1) // 2) * 8
     if not _f16():
         if twin is not None:
             return twin, twin.shape[1] * 4
@@ -1011,8 +1017,9 @@ def convt_c1_tc(inputs, m, sigmoid=False):
     """ConvTranspose3d(Cin -> 1, k4, s2, p1) over the channel concatenation of `inputs` on the tensor cores (MODE 4);
     NCDHW [B,1,2D,2H,2W] or None if not covered."""
     x0 = inputs[0]
-    if _x3() or _x2():
-        return None   # fp32 wanted: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and cheaper than the split-operand MMAs
+    if _x3():
+        return None   # 3xTF32: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and cheaper than 3x the TF32 MMAs (the fp16 hi/lo
+                      # mode below costs 2 MMAs of K = 16: measured faster than the stencil)
     if not ("convt_c1_tc" in POLICY and ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
             and tuple(m.padding) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1)
             and m.groups == 1 and m.out_channels == 1 and len(inputs) <= 2
@@ -1036,8 +1043,8 @@ def convt_c1_tc(inputs, m, sigmoid=False):
             bias = m.__dict__["_gb_zero_bias"] = torch.zeros(1, device=x0.device)
     out = torch.empty((b, 1, 2 * d, 2 * h, 2 * w), device=x0.device, dtype=torch.float32)
     s1 = ops[1][0] if len(ops) > 1 else None
-    _lib.call("genre_b200_convt_c1_tc_forward", ops[0][0].data_ptr(), ops[0][0].shape[1], s1.data_ptr() if s1 is not None else None,
-              s1.shape[1] if s1 is not None else 0, b, d, h, w, wpack.data_ptr(), 1 if g == 8 else 0, bias.data_ptr(),
+    _lib.call("genre_b200_convt_c1_tc_forward", ops[0][0].data_ptr(), ops[0][0].shape[1] // _parts(), s1.data_ptr() if s1 is not None else None,
+              s1.shape[1] // _parts() if s1 is not None else 0, b, d, h, w, wpack.data_ptr(), _op_flag() if g == 8 else 0, bias.data_ptr(),
               1 if sigmoid else 0, out.data_ptr(), _lib.stream_ptr(out))
     return out
 
