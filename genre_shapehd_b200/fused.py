@@ -61,3 +61,33 @@ class GenRe3DGlue(torch.nn.Module):
         _lib.call("genre_b200_scale_clamp_strided", p.data_ptr(), b, r3, 1.0, self.lo, self.hi,
                   out.data_ptr() + 4 * r3, 2 * r3, st)
         return out
+
+
+@torch.no_grad()
+def genre_forward_fused(net, input_struct, glue=None):
+    """Batched, mesh-free GenRe inference: the same tensors as the frozen ``Net.forward`` (models/genre_full_model.py:116-132;
+    same keys, same values up to rounding) with the 3D glue of the callers folded into the kernels (``GenRe3DGlue``).
+
+    It also stands in for the published test path ``Model.forward_with_trimesh`` (genre_full_model.py:202-233), which renders the
+    spherical map on the CPU through marching cubes + trimesh ray casting (util_sph.py:36-57), needs batch size 1 and is not
+    differentiable: here the spherical map comes from the differentiable renderer, for any batch, on the device.
+
+    net: models.genre_full_model.Net (reference class, unmodified), eval mode.  Returns the dict of Net.forward."""
+    dn = net.depth_and_inpaint
+    if glue is None:
+        glue = getattr(net, "_gb_glue", None)
+        if glue is None or glue.grid.device != net.grid.device:
+            glue = GenRe3DGlue(margin=net.margin).to(net.grid.device)
+            net.__dict__["_gb_glue"] = glue
+    out = dn.net1(input_struct)                                              # depth_pred_with_sph_inpaint.py:115-119
+    abs_depth = dn.get_abs_depth(out, input_struct)                         # :133-142 (frozen method)
+    proj, sph_in = glue.project_and_render(abs_depth)                       # :120-126 cam_bp, clamp(proj * 50), render, sph_pad
+    out_2 = dn.net2(sph_in)
+    out["proj_depth"] = proj * glue.scale
+    out["pred_sph_partial"] = sph_in
+    out["pred_sph_full"] = out_2["spherical"]
+    refine_input = glue.refine_input(proj, out["pred_sph_full"])            # genre_full_model.py:125-127,134-143
+    out["pred_proj_sph_full"] = refine_input[:, 0:1]
+    out["pred_proj_depth"] = refine_input[:, 1:2]
+    out["pred_voxel"] = net.refine_net(refine_input)
+    return out

@@ -355,6 +355,19 @@ int genre_b200_blocked_split2_f16(const float *src, int cg4, int64_t BD, int64_t
  * torch.backends.cudnn.allow_tf32 is off, so that occupancies match the fp32 reference within 1e-4. */
 int genre_b200_blocked_split3(const float *src, int cg, int64_t BD, int64_t H, int64_t W, float *dst, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ground-truth surface voxels.  Replaces the per-sample CPU code of Model.preprocess
+ * (models/genre_full_model.py:86-96, scipy.ndimage.binary_erosion inside DataLoader workers):
+ *     val  = flip(transpose(voxel, (0,2,1)), 2)                      (transpose_flip != 0; :89-90)
+ *     out  = clip(val - binary_erosion(val != 0, ones((3,3,3)), iterations), 0, 1)   (:91-93, border value 0)
+ *   vox, out [N, R, R, R] dense fp32, distinct buffers; R a multiple of 32, at most 256; 1 <= iterations <= 15
+ *   workspace: genre_b200_voxel_surface_workspace_bytes(N, R) bytes (one bit per voxel), caller-owned
+ * Bit-exact against scipy (tests/test_gpu_toolbox.py).
+ * ------------------------------------------------------------------------------------------- */
+size_t genre_b200_voxel_surface_workspace_bytes(int64_t N, int res);
+int genre_b200_voxel_surface(const float *vox, int64_t N, int res, int iterations, int transpose_flip, float *out,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,3 +213,26 @@ def test_shapehd_training_step_runs_on_cuda(ref_root):
         assert (g_c[name] - g_r[name]).abs().max().item() <= 1e-2 * scale + 1e-6 * overall, name
     for p in net.d.parameters():
         assert p.grad is None            # D stays frozen (shapehd.py:104-105)
+
+
+@pytest.mark.gpu
+def test_fused_batched_forward_equals_the_frozen_forward(ref_root):
+    """genre_shapehd_b200.fused.genre_forward_fused (the batched, mesh-free stand-in for
+    forward_with_trimesh) returns the tensors of the frozen Net.forward"""
+    import models.genre_full_model as gfm
+    from genre_shapehd_b200.fused import genre_forward_fused
+    from genre_shapehd_b200.synth_genre import init_genre_net_for_bench
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    net = gfm.Net(genre_opt(), gfm.Model)
+    init_genre_net_for_bench(net)
+    net = net.to(dev).eval()
+    x = genre_inputs(3, dev, seed=4)
+    with torch.no_grad():
+        a = net(types.SimpleNamespace(rgb=x.rgb.clone(), silhou=x.silhou.clone()))
+        b = genre_forward_fused(net, types.SimpleNamespace(rgb=x.rgb.clone(), silhou=x.silhou.clone()))
+    for key in ("proj_depth", "pred_sph_partial", "pred_sph_full", "pred_proj_sph_full", "pred_proj_depth", "pred_voxel"):
+        assert a[key].shape == b[key].shape, key
+        scale = max(1.0, a[key].abs().max().item())
+        assert (a[key] - b[key]).abs().max().item() <= 2e-4 * scale, key
+    assert (a["pred_voxel"] - b["pred_voxel"]).abs().max().item() <= 1e-4 * max(1.0, a["pred_voxel"].abs().max().item())

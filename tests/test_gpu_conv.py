@@ -467,6 +467,24 @@ def test_gradient_penalty_double_backward_vs_cudnn(cin, cout, shape):
     assert (gw - rw).abs().max().item() <= 2e-2 * rw.abs().max().item()
 
 
+def test_double_backward_keeps_tiny_grad_of_grads():
+    """the grad-of-grad convolution of _ConvInputGrad must not run on fp16 operands: penalty gradients of 1e-5..1e-7
+    are subnormal / flushed in fp16.  The double backward of sum(gx * v) with |v| ~ 1e-6 equals the forward convolution of v;
+    relative error must stay at operand-rounding level whatever the magnitude."""
+    torch.manual_seed(77)
+    m = nets.Conv3d(64, 64, 4, 2, 1, bias=False).to(DEV)
+    x = torch.rand(1, 64, 4, 32, 32, device=DEV, requires_grad=True)
+    v = torch.randn_like(x) * 1e-6
+    out = m(x)
+    gy = torch.randn_like(out).requires_grad_(True)
+    (gx,) = torch.autograd.grad(out, x, gy, create_graph=True)
+    (ggy,) = torch.autograd.grad((gx * v).sum(), gy)             # = conv3d(v, W): tiny values through the custom forward kernel
+    with fp32_reference():
+        ref = F.conv3d(v, m.weight, None, 2, 1)
+    assert ref.abs().max().item() < 1e-4
+    assert (ggy - ref).abs().max().item() <= _tol() * ref.abs().max().item()
+
+
 @pytest.mark.skipif(not ops_conv.TC_BACKWARD, reason="tensor-core input gradients switched off (GENRE_B200_CONV_TC_BACKWARD=0)")
 @pytest.mark.parametrize("kind,cin,cout,shape", [("convt", 80, 20, (1, 2, 32, 32)), ("conv", 2, 20, (1, 4, 64, 64))])
 def test_tensor_core_input_gradients_of_the_k8_layers(kind, cin, cout, shape):

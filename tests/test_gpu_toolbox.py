@@ -317,6 +317,20 @@ def test_calc_prob_vs_oracle(oracle, shape):
 
 
 @needs_ref
+def test_calc_prob_backward_is_finite_when_the_last_sample_is_certain():
+    """p[Z-1] == 1 made the last sample's gradient 0/0; the reference special-cases it as w/p (calc_prob_kernel.cu:169-172)"""
+    p = torch.rand(3, 1, 4, 4, 64, device=DEV).clamp_(0.05, 0.95)
+    p[..., -1] = 1.0
+    p.requires_grad_(True)
+    s = CalcStopProb.apply(p)
+    g = torch.rand_like(s)
+    (gp,) = torch.autograd.grad(s, p, g)
+    assert torch.isfinite(gp).all()
+    # last sample: d s_last / d p_last = prod_{k<last}(1 - p_k), nothing follows it
+    trans = torch.cumprod(1 - p.detach(), dim=-1)[..., -2]
+    assert torch.allclose(gp[..., -1], g[..., -1] * trans, rtol=1e-4, atol=1e-7)
+
+
 def test_calc_prob_vs_reference_kernels_full_size():
     gen = torch.Generator(DEV).manual_seed(0)
     p = torch.rand(2, 1, 128, 128, 256, device=DEV, generator=gen).clamp_(1e-5, 1 - 1e-5)
@@ -522,3 +536,31 @@ def test_bad_arguments_raise_runtime_error():
     with pytest.raises(RuntimeError):
         _lib.call("genre_b200_cam_bp_forward", d.data_ptr(), 1, 1, 8, 8, 64, 64, 8, 1, d.data_ptr(), 1, 1,
                   d.data_ptr(), 1, 1, d.data_ptr(), None, 8, 0, d.data_ptr(), 16, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# ground-truth surface voxels: Model.preprocess of genre_full_model.py:86-96 on the GPU
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("res,iters,xform", [(128, 2, True), (64, 2, True), (32, 1, False), (96, 3, True), (128, 2, False)])
+def test_voxel_surface_equals_scipy_binary_erosion(res, iters, xform):
+    """bit-exact against the reference's own call: val - binary_erosion(val, ones((3,3,3)), iterations) after the transpose + flip"""
+    from scipy.ndimage import binary_erosion
+    from genre_shapehd_b200.postprocess import voxel_surface
+    rng = np.random.RandomState(res + iters)
+    c = (np.arange(res) + 0.5) / res - 0.5
+    X, Y, Z = np.meshgrid(c, c, c, indexing="ij")
+    vols = []
+    for i in range(3):
+        solid = ((X - 0.05 * i) ** 2 / 0.16 + Y ** 2 / 0.09 + (Z + 0.1 * i) ** 2 / 0.2) < 1.0           # an ellipsoid ...
+        solid |= (np.abs(X) < 0.45) & (np.abs(Y + 0.3) < 0.06) & (np.abs(Z) < 0.49)                     # ... a slab touching the border
+        solid &= rng.rand(res, res, res) > 0.002                                                       # ... with pin holes
+        vols.append(solid.astype(np.float32))
+    vols[2][0, :, :] = 1.0                                                                             # a face of the volume
+    v = np.stack(vols)[:, None]
+    out = voxel_surface(torch.from_numpy(v).to(DEV), iterations=iters, transpose_flip=xform).cpu().numpy()
+    for i in range(3):
+        val = v[i, 0]
+        if xform:
+            val = np.flip(np.transpose(val, (0, 2, 1)), 2)
+        want = np.clip(val - binary_erosion(val, structure=np.ones((3, 3, 3)), iterations=iters).astype(float), 0, 1)
+        assert np.array_equal(out[i, 0], want.astype(np.float32)), i
