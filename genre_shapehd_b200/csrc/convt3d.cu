@@ -675,7 +675,9 @@ static int launch_convt_merged(const ConvTParams &p, cudaStream_t st) {
 }
 template <int MT>
 static int launch_convt_c1(const ConvTParams &p, cudaStream_t st) {
-  return launch_convt_op<3, 3, 16, MT, 4>(p, st);
+  if (g_conv_op == 2)   // not routed (ops_conv.convt_c1_tc): the exact FP32-pipe stencil serves the fp32-accurate modes
+    return fail_arg(GENRE_B200_EINVAL, "convt_c1_tc: the fp16 hi/lo operand mode is not supported for the 1-channel layer");
+  return g_conv_op == 1 ? launch_convt_impl<3, 3, 16, MT, 4, 1>(p, st) : launch_convt_impl<3, 3, 16, MT, 4, 0>(p, st);
 }
 template <int T, int NPAD, int MT>
 static int launch_conv_merged8(const ConvTParams &p, cudaStream_t st) {

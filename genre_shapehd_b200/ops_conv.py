@@ -1017,9 +1017,9 @@ def convt_c1_tc(inputs, m, sigmoid=False):
     """ConvTranspose3d(Cin -> 1, k4, s2, p1) over the channel concatenation of `inputs` on the tensor cores (MODE 4);
     NCDHW [B,1,2D,2H,2W] or None if not covered."""
     x0 = inputs[0]
-    if _x3():
-        return None   # 3xTF32: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and cheaper than 3x the TF32 MMAs (the fp16 hi/lo
-                      # mode below costs 2 MMAs of K = 16: measured faster than the stencil)
+    if _x3() or _x2():
+        return None   # fp32 wanted: the FP32-pipe stencil (csrc/convt_c1.cu) is exact and, measured, faster than the split-operand
+                      # MMAs once the operand split of its two 336 MB sources is paid (Unet_3D.dec6: 1.33 vs 1.79 ms at B=16)
     if not ("convt_c1_tc" in POLICY and ENABLED and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
             and tuple(m.padding) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1)
             and m.groups == 1 and m.out_channels == 1 and len(inputs) <= 2

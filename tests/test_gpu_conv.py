@@ -237,8 +237,8 @@ def test_convt_one_output_channel_vs_torch(cin, b, d, h, w):
 def test_convt_c1_tensor_core_vs_torch(chans, b, d, h, w, sigmoid):
     """MODE 4: ConvT(Cin -> 1) as 27 union taps x 8 output classes on the tensor cores; one or two (skip) sources, the
     20-channel ones arriving as blocked twins of a previous custom layer (zero-padded to the operand group size)"""
-    if ops_conv.PRECISION == "fp32x3":
-        pytest.skip("3xTF32: the 1-channel layer goes to the exact FP32-pipe kernel instead (test_dec6_two_source_path)")
+    if ops_conv.PRECISION in EXACT_MODES:
+        pytest.skip("fp32 wanted: the 1-channel layer goes to the exact FP32-pipe kernel instead (test_dec6_two_source_path)")
     torch.manual_seed(sum(chans) + w)
     m = nets.ConvTranspose3d(sum(chans), 1, 4, 2, 1).to(DEV)
     xs = []
