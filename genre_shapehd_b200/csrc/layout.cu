@@ -34,7 +34,39 @@ __device__ __forceinline__ void store_unit(void *dst, size_t unit_index, const f
   }
 }
 
-template <int G>
+// X2 output (the fp32-accurate conv mode's operand): [r][2 parts][CG][plane] units of 8 fp16, part 0 = hi = fp16(a), part 1 =
+// lo' = fp16((a - hi) * 2^11).  `u` is the unit index in the single-part layout [r][CG][plane]; units_per_r = CG * plane.
+__device__ __forceinline__ void store_unit_x2(void *dst, size_t u, size_t r, size_t units_per_r, const float (&x)[8]) {
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = __float2half_rn(x[i]);
+    lo[i] = __float2half_rn((x[i] - __half2float(hi[i])) * 2048.0f);
+  }
+  uint4 ph, pl;
+  ph.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+  ph.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+  ph.z = (uint32_t)__half_as_ushort(hi[4]) | ((uint32_t)__half_as_ushort(hi[5]) << 16);
+  ph.w = (uint32_t)__half_as_ushort(hi[6]) | ((uint32_t)__half_as_ushort(hi[7]) << 16);
+  pl.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+  pl.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+  pl.z = (uint32_t)__half_as_ushort(lo[4]) | ((uint32_t)__half_as_ushort(lo[5]) << 16);
+  pl.w = (uint32_t)__half_as_ushort(lo[6]) | ((uint32_t)__half_as_ushort(lo[7]) << 16);
+  uint4 *o = reinterpret_cast<uint4 *>(dst) + u + r * units_per_r;
+  o[0] = ph;
+  o[units_per_r] = pl;
+}
+template <int G, bool X2>
+__device__ __forceinline__ void store_out(void *dst, size_t u, size_t r, size_t units_per_r, const float (&x)[G]) {
+  if constexpr (X2) {
+    static_assert(G == 8, "the hi/lo operand has 8 channels per unit");
+    store_unit_x2(dst, u, r, units_per_r, x);
+  } else {
+    store_unit<G>(dst, u, x);
+  }
+}
+
+template <int G, bool X2 = false>
 __global__ void __launch_bounds__(LY_THREADS)
 to_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t units) {
   const int CG = C / G;
@@ -49,12 +81,12 @@ to_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, 
     float x[G];
 #pragma unroll
     for (int e = 0; e < G; ++e) x[e] = __ldg(s + e * vol);
-    store_unit<G>(dst, u, x);
+    store_out<G, X2>(dst, u, r, (size_t)CG * plane, x);
   }
 }
 
 // one thread = one output position (z', y', x') of one input channel c: reads the 2x2x2 cell as four float2
-template <int G>
+template <int G, bool X2 = false>
 __global__ void __launch_bounds__(LY_THREADS)
 s2d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t cells,
                    int CGo /* channel groups of dst (>= C*8/G; the extra ones were zero-filled by the launcher) */) {
@@ -81,7 +113,7 @@ s2d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C,
       float x[G];
 #pragma unroll
       for (int e = 0; e < G; ++e) x[e] = v[e % 8];
-      store_unit<G>(dst, ((r * CGo + c) * H2 + y2) * (size_t)W2 + x2, x);
+      store_out<G, X2>(dst, ((r * CGo + c) * H2 + y2) * (size_t)W2 + x2, r, (size_t)CGo * H2 * W2, x);
     } else {
 #pragma unroll
       for (int pz = 0; pz < 2; ++pz) {
@@ -95,7 +127,7 @@ s2d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C,
 }
 
 // one thread = (z', pz, py, channel group, y', x'): reads G float2 (both x parities), writes the px = 0 and 1 units
-template <int G>
+template <int G, bool X2 = false>
 __global__ void __launch_bounds__(LY_THREADS)
 s2d_sources_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int cpad, int D, int H, int W,
                    size_t items) {
@@ -122,13 +154,13 @@ s2d_sources_kernel(const float *__restrict__ src, void *__restrict__ dst, int C,
       x1[e] = t.y;
     }
     const size_t u = ((r * (8 * CGs) + (size_t)(pzy * 2) * CGs + cg) * H2 + y2) * (size_t)W2 + x2;
-    store_unit<G>(dst, u, x0);
-    store_unit<G>(dst, u + (size_t)CGs * H2 * W2, x1);
+    store_out<G, X2>(dst, u, r, (size_t)8 * CGs * H2 * W2, x0);
+    store_out<G, X2>(dst, u + (size_t)CGs * H2 * W2, r, (size_t)8 * CGs * H2 * W2, x1);
   }
 }
 
 // 4x space-to-depth: one thread = one 16-byte unit = 8/G rows of 4 consecutive x of one (c, rz) plane
-template <int G>
+template <int G, bool X2 = false>
 __global__ void __launch_bounds__(LY_THREADS)
 s4d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C, int D, int H, int W, size_t units) {
   const int D4 = D / 4, H4 = H / 4, W4 = W / 4;
@@ -153,7 +185,7 @@ s4d_blocked_kernel(const float *__restrict__ src, void *__restrict__ dst, int C,
       x[row * 4 + 2] = t.z;
       x[row * 4 + 3] = t.w;
     }
-    store_unit<G>(dst, u, x);
+    store_out<G, X2>(dst, u, r, (size_t)CGo * H4 * W4, x);
   }
 }
 
@@ -284,16 +316,21 @@ split2_f16_kernel(const float4 *__restrict__ src, uint4 *__restrict__ dst, int c
 // 3: s4d_blocked.
 // group 4 -> fp32 units, 8 -> fp16 units.  src is contiguous NCDHW fp32.
 extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t C, int64_t D, int64_t H, int64_t W,
-                                           int mode, int group, int cpad, void *dst, void *stream) {
+                                           int mode, int group_in, int cpad, void *dst, void *stream) {
+  int group = group_in;
   GB_REQUIRE(src && dst, GENRE_B200_EINVAL, "to_blocked: null pointer");
   GB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, GENRE_B200_EINVAL, "to_blocked: empty tensor");
-  GB_REQUIRE(group == 4 || group == 8, GENRE_B200_EINVAL, "to_blocked: group must be 4 (fp32) or 8 (fp16)");
+  GB_REQUIRE(group == 4 || group == 8 || group == 16, GENRE_B200_EINVAL,
+             "to_blocked: group must be 4 (fp32), 8 (fp16) or 16 (fp16 hi/lo parts of 8 channels: dst [B*D'][2][cg][H'][W'][8])");
+  const bool x2 = group == 16;
+  if (x2) group = 8;
   GB_REQUIRE(aligned16(dst), GENRE_B200_EALIGN, "to_blocked: dst must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (mode == 0) {
     GB_REQUIRE(C % group == 0, GENRE_B200_EINVAL, "to_blocked: C=%lld not a multiple of %d", (long long)C, group);
     const size_t units = (size_t)(B * D * (C / group) * H * W);
     if (group == 4) to_blocked_kernel<4><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
+    else if (x2) to_blocked_kernel<8, true><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
     else to_blocked_kernel<8><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
     return check_launch("to_blocked kernel");
   }
@@ -305,10 +342,11 @@ extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t 
     if (cpad > C * 8) {  // pad the 8C space-to-depth channels with zero groups up to cpad channels
       GB_REQUIRE(cpad % group == 0, GENRE_B200_EINVAL, "s2d_blocked: cpad=%d not a multiple of %d", cpad, group);
       cgo = cpad / group;
-      cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)(B * (D / 2)) * cgo * (size_t)((H / 2) * (W / 2)) * 16, st);
+      cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)(B * (D / 2)) * cgo * (size_t)((H / 2) * (W / 2)) * 16 * (x2 ? 2 : 1), st);
       if (e != cudaSuccess) return fail_arg((int)e, "s2d_blocked: memset: %s", cudaGetErrorString(e));
     }
     if (group == 4) s2d_blocked_kernel<4><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells, cgo);
+    else if (x2) s2d_blocked_kernel<8, true><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells, cgo);
     else s2d_blocked_kernel<8><<<ly_grid(cells), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, cells, cgo);
     return check_launch("s2d_blocked kernel");
   }
@@ -317,6 +355,7 @@ extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t 
                "4x space-to-depth: extents must be multiples of 4 and src 16-byte aligned");
     const size_t units = (size_t)(B * C * 64 / group * (D / 4) * (H / 4) * (W / 4));
     if (group == 4) s4d_blocked_kernel<4><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
+    else if (x2) s4d_blocked_kernel<8, true><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
     else s4d_blocked_kernel<8><<<ly_grid(units), LY_THREADS, 0, st>>>(src, dst, (int)C, (int)D, (int)H, (int)W, units);
     return check_launch("s4d_blocked kernel");
   }
@@ -324,6 +363,7 @@ extern "C" int genre_b200_ncdhw_to_blocked(const float *src, int64_t B, int64_t 
   GB_REQUIRE(cpad >= C && cpad % group == 0, GENRE_B200_EINVAL, "s2d_sources: cpad=%d must be >= C and a multiple of %d", cpad, group);
   const size_t items = (size_t)(B * (D / 2) * 4 * (cpad / group) * (H / 2) * (W / 2));
   if (group == 4) s2d_sources_kernel<4><<<ly_grid(items), LY_THREADS, 0, st>>>(src, dst, (int)C, cpad, (int)D, (int)H, (int)W, items);
+  else if (x2) s2d_sources_kernel<8, true><<<ly_grid(items), LY_THREADS, 0, st>>>(src, dst, (int)C, cpad, (int)D, (int)H, (int)W, items);
   else s2d_sources_kernel<8><<<ly_grid(items), LY_THREADS, 0, st>>>(src, dst, (int)C, cpad, (int)D, (int)H, (int)W, items);
   return check_launch("s2d_sources kernel");
 }

@@ -217,9 +217,15 @@ def _act_group():
 
 
 def _on_device(x, group, dtype):
-    """the CUDA layout kernels (csrc/layout.cu) take contiguous fp32 NCDHW and write fp32 groups of 4 or fp16 groups of 8"""
+    """the CUDA layout kernels (csrc/layout.cu) take contiguous fp32 NCDHW and write fp32 groups of 4, fp16 groups of 8, or
+    (group 16) the fp16 hi/lo parts of groups of 8 channels"""
     return (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-            and ((group == 4 and dtype in (None, torch.float32)) or (group == 8 and dtype == torch.float16)))
+            and ((group == 4 and dtype in (None, torch.float32)) or (group in (8, 16) and dtype == torch.float16)))
+
+
+def _x2_direct(x):
+    """can the NCDHW -> hi/lo operand conversion run as one pass of the layout kernels?"""
+    return _x2() and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
 
 
 def _permuted_copy(view, dtype):
@@ -232,6 +238,10 @@ def _permuted_copy(view, dtype):
 def to_blocked(x, group=4, dtype=None):
     """NCDHW [B,C,D,H,W] (C % group == 0) -> [B*D, C/group, H, W, group] contiguous (optionally cast)."""
     b, c, d, h, w = x.shape
+    if group == 16:     # hi | lo' parts of groups of 8 channels (the f16x2 operand), CUDA only
+        out = torch.empty((b * d, 2 * (c // 8), h, w, 8), device=x.device, dtype=torch.float16)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 0, 16, 0, out.data_ptr(), _lib.stream_ptr(x))
+        return out
     if _on_device(x, group, dtype):
         out = torch.empty((b * d, c // group, h, w, group), device=x.device, dtype=dtype or x.dtype)
         _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 0, group, 0, out.data_ptr(), _lib.stream_ptr(x))
@@ -245,6 +255,8 @@ def _to_operand(x):
         twin = _cached_blocked(x)
         if twin is not None and twin.shape[1] * 4 == x.shape[1] and twin.shape[0] == x.shape[0] * x.shape[2]:
             return _split2(twin)
+        if _x2_direct(x) and x.shape[1] % 8 == 0:
+            return to_blocked(x, 16, torch.float16)
         return _split2(to_blocked(x, 4))
     return to_blocked(x, 8, torch.float16) if _f16() else to_blocked(x, 4)
 
@@ -478,6 +490,12 @@ def space_to_depth_blocked(x, group=4, dtype=None, cpad=0):
     """NCDHW [B,C,D,H,W] (even extents, group | 8) -> blocked [B*D/2, C*8/group, H/2, W/2, group] whose channel
     index is ((c*2 + pz)*2 + py)*2 + px for input position (2z'+pz, 2y'+py, 2x'+px); cpad > 8C appends zero channels."""
     b, c, d, h, w = x.shape
+    if group == 16:
+        ncg = max(c * 8, cpad) // 8
+        out = torch.empty((b * (d // 2), 2 * ncg, h // 2, w // 2, 8), device=x.device, dtype=torch.float16)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 1, 16, cpad if cpad > c * 8 else 0,
+                  out.data_ptr(), _lib.stream_ptr(x))
+        return out
     assert 8 % group == 0
     if _on_device(x, group, dtype):
         ncg = max(c * 8, cpad) // group
@@ -503,6 +521,10 @@ def space_to_depth4_blocked(x, group=4, dtype=None):
     """NCDHW [B,C,D,H,W] (extents % 4 == 0) -> blocked [B*D/4, 64C/group, H/4, W/4, group], channel index
     ((c*4 + rz)*4 + ry)*4 + rx for input position (4z'+rz, 4y'+ry, 4x'+rx)."""
     b, c, d, h, w = x.shape
+    if group == 16:
+        out = torch.empty((b * (d // 4), 2 * (c * 64 // 8), h // 4, w // 4, 8), device=x.device, dtype=torch.float16)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 3, 16, 0, out.data_ptr(), _lib.stream_ptr(x))
+        return out
     out_shape = (b * (d // 4), c * 64 // group, h // 4, w // 4, group)
     if _on_device(x, group, dtype):
         out = torch.empty(out_shape, device=x.device, dtype=dtype or x.dtype)
@@ -579,7 +601,10 @@ def _conv_k4s2_s2d(x, m, bn, slope):
         return None
     cpad = -(-x.shape[1] * 8 // (2 * g)) * 2 * g          # the 8*Cin channels rounded up to whole K chunks
     wpack = _pack(m, ("k4s2_s2d", cpad, npad, g), lambda w: pack_conv_k4s2_s2d_weights(w, cpad, npad, g), 1)
-    xb = _finish_operand(space_to_depth_blocked(x, _act_group(), torch.float16 if _f16() else None, cpad))
+    if _x2_direct(x):
+        xb = space_to_depth_blocked(x, 16, torch.float16, cpad)
+    else:
+        xb = _finish_operand(space_to_depth_blocked(x, _act_group(), torch.float16 if _f16() else None, cpad))
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
     cgo = (cout + 3) // 4
@@ -636,6 +661,10 @@ def space_to_depth_sources(x, cpad, group, dtype):
     other along the channel-group axis (sub-volume s = (pz*2+py)*2+px holds in[2z'+pz, 2y'+py, 2x'+px]), each zero-padded
     from C to cpad channels."""
     b, c, d, h, w = x.shape
+    if group == 16:
+        out = torch.empty((b * (d // 2), 2 * 8 * (cpad // 8), h // 2, w // 2, 8), device=x.device, dtype=torch.float16)
+        _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 2, 16, cpad, out.data_ptr(), _lib.stream_ptr(x))
+        return out
     if _on_device(x, group, dtype):
         out = torch.empty((b * (d // 2), 8 * (cpad // group), h // 2, w // 2, group), device=x.device, dtype=dtype or x.dtype)
         _lib.call("genre_b200_ncdhw_to_blocked", x.data_ptr(), b, c, d, h, w, 2, group, cpad, out.data_ptr(), _lib.stream_ptr(x))
@@ -714,7 +743,10 @@ def _conv_k4s2(x, m, bn, slope):
     cin = x.shape[1]
     cpad = (cin + 2 * g - 1) // (2 * g) * (2 * g)      # a K chunk (2 channel groups) must not straddle sub-volumes
     wpack = _pack(m, ("k4s2", cpad, npad, g), lambda w: pack_conv_k4s2_weights(w, cpad, npad, g), 1)
-    xb = _finish_operand(space_to_depth_sources(x, cpad, _act_group(), torch.float16 if _f16() else None))
+    if _x2_direct(x):
+        xb = space_to_depth_sources(x, cpad, 16, torch.float16)
+    else:
+        xb = _finish_operand(space_to_depth_sources(x, cpad, _act_group(), torch.float16 if _f16() else None))
     b = x.shape[0]
     bd, _, h, wd, _ = xb.shape
     cgo = (cout + 3) // 4
@@ -965,7 +997,10 @@ def conv3d(x, m, bn=None, slope=None):
         split_z = S4D_SPLIT_Z or _x2()     # f16x2 doubles the accumulator columns: 8 classes x 20 x 2 = 320 > 256, 4 classes fit
         wpack = _pack(m, ("k8s2_s4d", 20, g, split_z), lambda wt: pack_conv_k8s2_s4d_weights(wt, 20, g, split_z),
                       2 if split_z else 1)
-        xb = _finish_operand(space_to_depth4_blocked(x, _act_group(), torch.float16 if _f16() else None))
+        if _x2_direct(x):
+            xb = space_to_depth4_blocked(x, 16, torch.float16)
+        else:
+            xb = _finish_operand(space_to_depth4_blocked(x, _act_group(), torch.float16 if _f16() else None))
         bd, cg, h, w, _ = xb.shape
         cgo = (cout + 3) // 4
         out = torch.empty((bd * 2, cgo, 2 * h, 2 * w, 4), device=x.device, dtype=torch.float32)
@@ -979,7 +1014,10 @@ def conv3d(x, m, bn=None, slope=None):
         return None
     sc, sh = aff
     dev = x.device
-    xb = _finish_operand(space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x))
+    if _x2_direct(x):
+        xb = space_to_depth_blocked(x, 16, torch.float16)
+    else:
+        xb = _finish_operand(space_to_depth_blocked(x, 8, torch.float16) if _f16() else space_to_depth_blocked(x))
     b = x.shape[0]
     bd, cg, h, w, _ = xb.shape
     cgo = (cout + 3) // 4

@@ -261,8 +261,8 @@ def test_operand_mode_selection():
             torch.backends.cudnn.allow_tf32 = False
             assert ops_conv._mode() == ops_conv.EXACT_IMPL
             torch.backends.cudnn.allow_tf32 = True
-        with ops_conv._forced_mode("tf32"):                          # ... and never a downgrade of the exact mode
-            assert ops_conv._mode() == ops_conv.EXACT_IMPL
+        with ops_conv._forced_mode("tf32"):                          # ... and never a downgrade of the exact mode: gradient
+            assert ops_conv._mode() == "fp32x3"                      # convolutions take the split with fp32's exponent range
         with ops_conv.precision("fp32x3"):
             assert ops_conv._mode() == "fp32x3" and ops_conv._x3() and ops_conv._group() == 4
         ops_conv.PRECISION = "tf32"

@@ -557,3 +557,21 @@ def test_f16x2_matches_fp32_much_closer_than_single_pass():
             assert y is not None
             errs[mode] = ((y - ref).abs().max() / ref.abs().max()).item()
     assert errs["f16x2"] <= 2e-5 and errs["f16x2"] < errs["f16"] / 20, errs
+
+
+def test_direct_hi_lo_conversions_equal_convert_then_split():
+    """csrc/layout.cu with group code 16 (NCDHW -> hi/lo operand in ONE pass) against the two-pass route (fp32 blocked, then
+    split2_f16): bit-identical for the plain, 2x space-to-depth, parity-sub-volume and 4x space-to-depth layouts"""
+    torch.manual_seed(13)
+    x = torch.randn(2, 16, 6, 16, 24, device=DEV) * 3
+    assert torch.equal(ops_conv.to_blocked(x, 16, torch.float16), ops_conv._split2(ops_conv.to_blocked(x, 4)))
+    x2 = torch.randn(3, 2, 4, 6, 8, device=DEV)
+    for cpad in (0, 32):
+        assert torch.equal(ops_conv.space_to_depth_blocked(x2, 16, torch.float16, cpad),
+                           ops_conv._split2(ops_conv.space_to_depth_blocked(x2, 4, None, cpad)))
+    x3 = torch.randn(2, 20, 4, 6, 8, device=DEV)
+    assert torch.equal(ops_conv.space_to_depth_sources(x3, 32, 16, torch.float16),
+                       ops_conv._split2(ops_conv.space_to_depth_sources(x3, 32, 4, None)))
+    x4 = torch.randn(2, 2, 8, 4, 12, device=DEV)
+    assert torch.equal(ops_conv.space_to_depth4_blocked(x4, 16, torch.float16),
+                       ops_conv._split2(ops_conv.space_to_depth4_blocked(x4, 4, None)))

@@ -564,3 +564,72 @@ def test_voxel_surface_equals_scipy_binary_erosion(res, iters, xform):
             val = np.flip(np.transpose(val, (0, 2, 1)), 2)
         want = np.clip(val - binary_erosion(val, structure=np.ones((3, 3, 3)), iterations=iters).astype(float), 0, 1)
         assert np.array_equal(out[i, 0], want.astype(np.float32)), i
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE full sizes: size-independent properties (the oracle runs in seconds only at small sizes)
+# --------------------------------------------------------------------------------------------------
+def test_cam_bp_full_batch32_checksums_and_batch_equivariance(oracle):
+    """BASELINE configs[1] size (32 x 256x256 -> 128^3): per-map hit count = number of in-bounds foreground pixels (the oracle's
+    bit-exact voxel indices), background voxels exactly 0, hit voxels in (0.13, 1], and permuting the batch permutes the
+    output bit for bit (integer accumulation: no run-to-run or placement dependence)"""
+    from genre_shapehd_b200.synth import bench_depth_batch
+    d = bench_depth_batch(32)
+    x = torch.from_numpy(d).to(DEV)
+    layer = Camera_back_projection_layer()
+    out = layer(x)
+    idx = oracle.cam_bp_voxel_index(d, 418.3, 2.2, 128)              # [32,1,256,256] int32, -1 = skipped / out of bounds
+    for n in (0, 1, 17, 31):
+        hit = np.unique(idx[n][idx[n] >= 0])
+        got = torch.nonzero(out[n].reshape(-1)).reshape(-1).cpu().numpy()
+        assert np.array_equal(got, hit)
+    hitv = out[out != 0]
+    assert hitv.min().item() > 0.13 and hitv.max().item() <= 1.0
+    perm = torch.randperm(32, device=DEV)
+    assert torch.equal(layer(x[perm]), out[perm])
+    assert torch.equal(layer(x), out)                                 # and run to run
+
+
+def test_calc_prob_full_size_conserves_probability():
+    """[16,1,128,128,256] (the GenRe size): sum_z stop_prob + prod_z (1 - p) == 1 for every ray"""
+    gen = torch.Generator(DEV).manual_seed(4)
+    p = torch.rand(16, 1, 128, 128, 256, device=DEV, generator=gen).pow_(6).clamp_(1e-5, 1 - 1e-5)
+    s = CalcStopProb.apply(p)
+    total = s.sum(-1, dtype=torch.float64) + torch.prod(1 - p.double(), dim=-1)
+    assert (total - 1).abs().max().item() < 2e-5
+    assert (s >= 0).all()
+
+
+def test_render_and_sph_bp_batch_equivariance_full_size():
+    """B=16 at GenRe sizes: the renderer (per-volume brick masks, strided ray groups) and the spherical back-projection give
+    bit-identical per-sample results whatever the sample's position in the batch"""
+    d = np.stack([sphere_depth(radius=0.3 + 0.008 * i) for i in range(16)])[:, None]
+    vox = torch.clamp(Camera_back_projection_layer()(torch.from_numpy(d).to(DEV)) * 50, 1e-5, 1 - 1e-5)
+    m = render_spherical().to(DEV)
+    sph = m(vox)
+    perm = torch.randperm(16, device=DEV)
+    assert torch.equal(m(vox[perm]), sph[perm])
+    assert torch.equal(m(vox[3:4]), sph[3:4])                         # batch 1: a different CTA count per volume
+    grid = gen_sph_grid().to(DEV).expand(16, -1, -1, -1, -1)
+    tdf, cnt = SphericalBackProjection.apply(1 - sph, grid, 128)
+    tdf_p, cnt_p = SphericalBackProjection.apply((1 - sph)[perm].contiguous(), grid, 128)
+    assert torch.equal(tdf_p, tdf[perm]) and torch.equal(cnt_p, cnt[perm])
+    assert int(cnt.sum().item()) <= 16 * 128 * 128 and cnt.max().item() >= 1
+
+
+def test_nnd_full_size_symmetry_and_minimality():
+    """[4,16384,3] (BASELINE configs[4]): direction 1 of (a, b) is direction 2 of (b, a) bit for bit, every reported distance is
+    the distance to the reported index, and no sampled candidate is closer"""
+    gen = torch.Generator(DEV).manual_seed(9)
+    a = torch.rand(4, 16384, 3, device=DEV, generator=gen) - 0.5
+    b = torch.rand(4, 16384, 3, device=DEV, generator=gen) - 0.5
+    d1, d2, i1, i2 = NNDFunction.apply(a, b)
+    e1, e2, j1, j2 = NNDFunction.apply(b, a)
+    assert torch.equal(d1, e2) and torch.equal(d2, e1) and torch.equal(i1, j2) and torch.equal(i2, j1)
+    nb = torch.gather(b, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))
+    diff = nb - a
+    recomputed = torch.addcmul(torch.addcmul(diff[..., 1] * diff[..., 1], diff[..., 0], diff[..., 0]), diff[..., 2], diff[..., 2])
+    assert (recomputed - d1).abs().max().item() <= 1e-9
+    probe = b[:, torch.randint(0, 16384, (256,), device=DEV, generator=gen)]          # [4,256,3]
+    dp = ((a.unsqueeze(2) - probe.unsqueeze(1)) ** 2).sum(-1).min(-1).values
+    assert (d1 <= dp + 1e-7).all()
