@@ -113,6 +113,17 @@ def _mode():
     return _FORCED_MODE or base
 
 
+def cudnn_precision():
+    """cuDNN flags for convolutions this module hands to cuDNN (layers / gradients without a custom kernel): in the fp32-accurate
+    modes they must not silently drop to TF32 because PyTorch's global default allows it; the single-pass modes leave the
+    caller's setting alone."""
+    import contextlib
+    if _mode() in ("f16x2", "fp32x3") and torch.backends.cudnn.allow_tf32:
+        return torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, benchmark=torch.backends.cudnn.benchmark,
+                                          deterministic=torch.backends.cudnn.deterministic, allow_tf32=False)
+    return contextlib.nullcontext()
+
+
 def describe_mode():
     m = _mode()
     return {"f16": "f16 single pass (10-bit operand mantissa, fp32 accumulate)", "tf32": "tf32 single pass (10-bit operand mantissa)",
@@ -771,7 +782,8 @@ class _ConvInputGrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gy, weight, x, m):
         conf = (list(m.stride), list(m.padding), list(m.dilation), False, [0, 0, 0], m.groups)
-        gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, *conf, [True, False, False])
+        with cudnn_precision():
+            gx, _, _ = torch.ops.aten.convolution_backward(gy, x, weight, None, *conf, [True, False, False])
         ctx.save_for_backward(gy, weight)
         ctx.m, ctx.conf = m, conf
         return gx
@@ -789,11 +801,13 @@ class _ConvInputGrad(torch.autograd.Function):
             with _forced_mode("tf32"):
                 g_gy = conv3d(ggx, m)
             if g_gy is None:
-                g_gy = torch.nn.functional.conv3d(ggx, weight, None, m.stride, m.padding, m.dilation, m.groups)
+                with cudnn_precision():
+                    g_gy = torch.nn.functional.conv3d(ggx, weight, None, m.stride, m.padding, m.dilation, m.groups)
             elif m.bias is not None:
                 g_gy = g_gy - m.bias.detach().view(1, -1, 1, 1, 1)
         if ctx.needs_input_grad[1]:
-            _, g_w, _ = torch.ops.aten.convolution_backward(gy, ggx, weight, None, *ctx.conf, [False, True, False])
+            with cudnn_precision():
+                _, g_w, _ = torch.ops.aten.convolution_backward(gy, ggx, weight, None, *ctx.conf, [False, True, False])
         return g_gy, g_w, None, None
 
 
@@ -910,8 +924,9 @@ class _ConvForward(torch.autograd.Function):
             gx_custom = _ConvInputGrad.apply(gy, weight, x, ctx.module)   # double backward stays on the custom forward
             mask[0] = False
         if any(mask):
-            gx, gw, gb = torch.ops.aten.convolution_backward(gy, x, weight, bias_sizes, list(stride), list(padding),
-                                                              list(dilation), transposed, list(out_pad), groups, mask)
+            with cudnn_precision():
+                gx, gw, gb = torch.ops.aten.convolution_backward(gy, x, weight, bias_sizes, list(stride), list(padding),
+                                                                  list(dilation), transposed, list(out_pad), groups, mask)
         return (gx_custom if gx_custom is not None else gx), (gw_custom if gw_custom is not None else gw), gb, None
 
 
