@@ -33,4 +33,5 @@ python profiles/bench_train_unet.py > $O/train_unet_exact.json 2>> $O/misc.err
 GENRE_B200_CONV_PRECISION=f16 python profiles/bench_train_unet.py > $O/train_unet_f16.json 2>> $O/misc.err
 GENRE_B200_CONV_PRECISION=f16 NCU=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file $O/train_unet_launches_f16.csv python profiles/bench_train_unet.py > /dev/null 2>> $O/ncu.err
-tail -n 4 $O/pytest_gpu.txt; head -c 600 $O/bench_n1.json; echo; tail -n 3 $O/bench_n1.err $O/misc.err $O/ncu.err
+python __graft_entry__.py smoke > $O/smoke.txt 2>&1
+tail -n 4 $O/pytest_gpu.txt; tail -n 2 $O/smoke.txt; head -c 600 $O/bench_n1.json; echo; tail -n 3 $O/bench_n1.err $O/misc.err $O/ncu.err
