@@ -156,7 +156,7 @@ cam_project_kernel(const CamProjArgs a) {
 }
 
 template <bool W_FAST>
-struct CamProjector {   // project stage of the pipelined kernel (voxelize.cuh vox_pipeline_kernel)
+struct CamProjector {   // project stage of the overlapped kernel (voxelize.cuh vox_overlap_kernel)
   using Args = CamProjArgs;
   static __device__ __forceinline__ void run(const Args &a, int bx, int map, unsigned *s_hist) {
     cam_project_body<W_FAST>(a, bx, map, s_hist);
@@ -396,16 +396,14 @@ extern "C" int genre_b200_cam_bp_forward(const float *depth, int64_t N, int64_t 
     bg = inv_r;
   }
   if (int rc = vox_clear_counts(w, N * C, st)) return rc;
-  if (flags & GENRE_B200_FLAG_PIPELINE) {
-    // experimental (off by default): chunked project|splat pipeline (voxelize.cuh).  Measured at batch 32: 67.6 / 69.8 / 75.3 us
-    // with 2 / 4 / 8 chunks against 68.0 us back to back: programmatic dependent launch starts a dependent grid only once
-    // every CTA of its predecessor has been scheduled, so the projection of the next chunk still runs in the tail
+  if (!(flags & GENRE_B200_FLAG_NO_OVERLAP)) {
+    // batches of 4+ maps: project and splat in ONE kernel with an interleaved block order (voxelize.cuh vox_overlap_kernel)
     CamProjArgs a;
     bool w_fast = true;
     if (int rc = cam_proj_args(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, &a, &w_fast)) return rc;
     const int gx = cam_proj_ctas_per_map(H * W);
-    const int rc = w_fast ? vox_pipeline<CamProjector<true>>(a, gx, w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st)
-                          : vox_pipeline<CamProjector<false>>(a, gx, w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st);
+    const int rc = w_fast ? vox_overlap<CamProjector<true>>(a, gx, w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st)
+                          : vox_overlap<CamProjector<false>>(a, gx, w, N * C, H * W, res, tdf, cnt, alpha, beta, bg, st);
     if (rc >= 0) return rc;
   }
   if (int rc = cam_project_launch(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, st)) return rc;

@@ -8,7 +8,8 @@ namespace gb {
 // ------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t counters_bytes(int64_t n_maps, size_t nt) { return align_up(((size_t)n_maps * nt + (size_t)n_maps) * 4, 256); }
+static size_t counters_words(int64_t n_maps, size_t nt) { return (size_t)n_maps * nt + (size_t)n_maps + (size_t)n_maps + 1; }
+static size_t counters_bytes(int64_t n_maps, size_t nt) { return align_up(counters_words(n_maps, nt) * 4, 256); }
 
 size_t vox_workspace_bytes(int64_t n_maps, int64_t P, int res) {
   const size_t nt = (size_t)vox_ntiles(res);
@@ -24,6 +25,7 @@ bool vox_carve(void *ws, size_t ws_bytes, int64_t n_maps, int64_t P, int res, Vo
   char *p = (char *)ws;
   out->counts = (unsigned *)p;
   out->ovf_count = out->counts + (size_t)n_maps * nt;
+  out->sync = out->ovf_count + (size_t)n_maps;
   p += counters_bytes(n_maps, nt);
   out->buckets = (uint2 *)p;
   p += align_up((size_t)n_maps * nt * VOX_BUCKET * 8, 256);
@@ -33,7 +35,7 @@ bool vox_carve(void *ws, size_t ws_bytes, int64_t n_maps, int64_t P, int res, Vo
 }
 
 int vox_clear_counts(const VoxWorkspace &w, int64_t n_maps, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(w.counts, 0, ((size_t)n_maps * w.ntiles + (size_t)n_maps) * 4, st);
+  cudaError_t e = cudaMemsetAsync(w.counts, 0, counters_words(n_maps, (size_t)w.ntiles) * 4, st);
   if (e != cudaSuccess) {
     set_error("voxelize: clearing tile counters: %s", cudaGetErrorString(e));
     return (int)e;

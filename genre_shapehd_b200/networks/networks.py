@@ -22,20 +22,14 @@ from torch import cat
 from genre_shapehd_b200 import ops_conv
 
 
-_cudnn_precision = ops_conv.cudnn_precision
-
-
 class Conv3d(nn.Conv3d):
     """nn.Conv3d parameters + dispatch of the CUDA forward to the sm_100a kernel when one covers the layer."""
 
     def forward(self, x):
         y = ops_conv.conv3d(x, self) if x.is_cuda else None
-        if y is not None:
-            return y
-        if not x.is_cuda:
-            return super().forward(x)
-        with _cudnn_precision():
-            return super().forward(x)
+        if y is None and x.is_cuda and self.padding_mode == "zeros":
+            y = ops_conv.exact_fallback(x, self, False)         # <= 8^3 layers in the fp32-accurate modes: 3xTF32 on cuDNN
+        return y if y is not None else super().forward(x)
 
 
 class ConvTranspose3d(nn.ConvTranspose3d):
@@ -43,12 +37,9 @@ class ConvTranspose3d(nn.ConvTranspose3d):
         y = ops_conv.conv_transpose3d(x, self) if output_size is None else None
         if y is None and output_size is None and x.is_cuda:
             y = ops_conv.gemm_conv(x, self)
-        if y is not None:
-            return y
-        if not x.is_cuda:
-            return super().forward(x, output_size)
-        with _cudnn_precision():
-            return super().forward(x, output_size)
+        if y is None and x.is_cuda and self.padding_mode == "zeros":
+            y = ops_conv.exact_fallback(x, self, True, output_size)
+        return y if y is not None else super().forward(x, output_size)
 
 
 class FusedSequential(nn.Sequential):

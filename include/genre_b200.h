@@ -35,8 +35,8 @@ extern "C" {
 
 /* flags for the projection entry points */
 #define GENRE_B200_FLAG_SHIFT_TDF 1u /* fuse Camera_back_projection_layer.shift_tdf: 1 - R*tdf */
-#define GENRE_B200_FLAG_PIPELINE 2u  /* cam_bp_forward, experimental: cut the batch into chunks and let one kernel carry the
-                                        projection of chunk c and the splat of chunk c-1 (measured on B200: no gain) */
+#define GENRE_B200_FLAG_NO_OVERLAP 2u  /* cam_bp_forward: run project and splat as two kernels back to back instead of the
+                                         one overlapped kernel (batches of 4+ maps); for A/B timing */
 
 const char *genre_b200_last_error(void);
 /* library/ABI version: major*1000 + minor */

@@ -45,11 +45,16 @@ def copy(name, dst=None):
 
 
 def ncu_rows(rep):
-    """rows (dicts) of one .ncu-rep, metric name -> 'value unit'"""
+    """rows (dicts) of one capture, metric name -> (value, unit); reads the raw CSV made on the GPU box (`ncu -i ... --page raw
+    --csv`, next to where the .ncu-rep was) or, if the report itself is here, converts it now"""
     p = os.path.join(SRC, rep)
-    if not os.path.exists(p):
+    raw = p[:-len(".ncu-rep")] + ".rawcsv"
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(p):
+        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    else:
         return []
-    out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return []

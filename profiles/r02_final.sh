@@ -17,11 +17,13 @@ for mode in exact f16; do
      --csv --log-file $O/unet_tensor_pipe_$mode.csv python profiles/unet_breakdown.py > /dev/null 2>> $O/ncu.err
 done
 # full captures: the conv kernel of dec5, the voxeliser, the renderer
-NCU=1 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:convt3d_s2_kernel -c 12 -o $O/prof_unet_convs python profiles/unet_breakdown.py > /dev/null 2>> $O/ncu.err
-NCU=1 ncu --profile-from-start off --set full --import-source on --clock-control none -o $O/prof_render python profiles/microbench_render.py > /dev/null 2>> $O/ncu.err
+NCU=1 ncu --profile-from-start off --set full --clock-control none -k regex:convt3d_s2_kernel -c 12 -o $O/prof_unet_convs python profiles/unet_breakdown.py > /dev/null 2>> $O/ncu.err
+NCU=1 ncu --profile-from-start off --set full --clock-control none -o $O/prof_render python profiles/microbench_render.py > /dev/null 2>> $O/ncu.err
 for k in nnd_forward calc_prob_forward calc_prob_backward sph_project vox_splat cam_project sph_bp_backward cam_bp_backward; do
   ncu --set full --clock-control none -k regex:$k --launch-skip 3 -c 1 -o $O/prof_op_$k python profiles/microbench_ops.py > /dev/null 2>> $O/ncu.err
 done
+# the reports are too large to travel back (64 MiB cap on gpurun_out/): keep their raw metric tables as CSV
+for f in $O/*.ncu-rep; do ncu -i $f --page raw --csv > ${f%.ncu-rep}.rawcsv 2>/dev/null; rm -f $f; done
 # per-layer / per-op / training timings
 python profiles/unet_breakdown.py > $O/unet_breakdown_exact.json 2>> $O/misc.err
 GENRE_B200_CONV_PRECISION=f16 python profiles/unet_breakdown.py > $O/unet_breakdown_f16.json 2>> $O/misc.err
