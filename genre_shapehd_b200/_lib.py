@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgenre_b200.so")
 
 FLAG_SHIFT_TDF = 1
-FLAG_NO_OVERLAP = 2   # cam_bp_forward: project and splat as two kernels instead of the overlapped one (GENRE_B200_CAM_BP_OVERLAP=0)
-CAM_BP_FLAGS = FLAG_NO_OVERLAP if os.environ.get("GENRE_B200_CAM_BP_OVERLAP", "1") == "0" else 0
+FLAG_OVERLAP = 2   # cam_bp_forward, experimental: project and splat overlapped in one kernel (GENRE_B200_CAM_BP_OVERLAP=1); measured slower
+CAM_BP_FLAGS = FLAG_OVERLAP if os.environ.get("GENRE_B200_CAM_BP_OVERLAP", "0") != "0" else 0
 
 _i64 = ctypes.c_int64
 _int = ctypes.c_int

@@ -396,8 +396,9 @@ extern "C" int genre_b200_cam_bp_forward(const float *depth, int64_t N, int64_t 
     bg = inv_r;
   }
   if (int rc = vox_clear_counts(w, N * C, st)) return rc;
-  if (!(flags & GENRE_B200_FLAG_NO_OVERLAP)) {
-    // batches of 4+ maps: project and splat in ONE kernel with an interleaved block order (voxelize.cuh vox_overlap_kernel)
+  if (flags & GENRE_B200_FLAG_OVERLAP) {
+    // experimental, off by default (measured slower): project and splat in ONE kernel with an interleaved block order
+    // (voxelize.cuh vox_overlap_kernel)
     CamProjArgs a;
     bool w_fast = true;
     if (int rc = cam_proj_args(depth, N, C, H, W, sN, sC, sH, sW, fl, fN, fC, camdist, dN, dC, res, w, &a, &w_fast)) return rc;

@@ -125,23 +125,30 @@ def exact_fallback(x, m, transposed, output_size=None):
     """Forward of a layer NO custom kernel covers (the <= 8^3 layers of the nets) in the fp32-accurate modes, inference only: cuDNN
     fp32 convolutions without tensor cores are 10-20x slower than its TF32 ones (Unet_3D's five small layers: 0.6 -> 11 ms at
     batch 16), and plain TF32 would put a 10-bit mantissa into an otherwise fp32-accurate network.  So the layer is evaluated as
-    the 3xTF32 operand split on cuDNN's TF32 kernels:  conv(x_hi, w_hi) + conv(x_hi, w_lo) + conv(x_lo, w_hi)  with hi = the
+    the 3xTF32 operand split on cuDNN's TF32 kernels:  conv(x_lo, w_hi) + conv(x_hi, [w_hi | w_lo])  with hi = the
     TF32 rounding (exactly representable: cuDNN's own operand conversion is then lossless) and fp32 accumulation.
     Returns None when not applicable (autograd, single-pass modes, TF32 disallowed globally -> plain cuDNN fp32)."""
     if not (x.is_cuda and x.dtype == torch.float32 and _mode() in ("f16x2", "fp32x3") and torch.backends.cudnn.allow_tf32
             and not _needs_grad(x, m.weight, m.bias) and output_size is None):
         return None
     f = torch.nn.functional
-    w = m.weight.detach()
-    xh, wh = _tf32_hi(x), _tf32_hi(w)
-    xl, wl = x - xh, w - wh
+    cdim = 1 if transposed else 0            # output-channel axis of the weight tensor
+
+    def split(w):                            # (W_hi | W_lo) stacked along the output channels, and W_hi: cached per weight version
+        wh = _tf32_hi(w)
+        return torch.cat((wh, w - wh), dim=cdim).contiguous(), wh
+    wcat, wh = _cached_pack(m, ("exact_fallback",), split)
+    xh = _tf32_hi(x)
+    xl = x - xh
     if transposed:
         conv = lambda a, b: f.conv_transpose3d(a, b, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
     else:
         conv = lambda a, b: f.conv3d(a, b, None, m.stride, m.padding, m.dilation, m.groups)
+    both = conv(xh, wcat)                    # x_hi * (W_hi | W_lo): one launch, 2 * Cout channels
+    c = m.out_channels
     y = conv(xl, wh)
-    y += conv(xh, wl)
-    y += conv(xh, wh)
+    y += both[:, c:]
+    y += both[:, :c]
     if m.bias is not None:
         y += m.bias.detach().view(1, -1, 1, 1, 1)
     return y

@@ -35,8 +35,9 @@ extern "C" {
 
 /* flags for the projection entry points */
 #define GENRE_B200_FLAG_SHIFT_TDF 1u /* fuse Camera_back_projection_layer.shift_tdf: 1 - R*tdf */
-#define GENRE_B200_FLAG_NO_OVERLAP 2u  /* cam_bp_forward: run project and splat as two kernels back to back instead of the
-                                         one overlapped kernel (batches of 4+ maps); for A/B timing */
+#define GENRE_B200_FLAG_OVERLAP 2u  /* cam_bp_forward, experimental: project and splat overlapped in ONE kernel (interleaved block
+                                      order, per-map completion counters).  Measured on B200: slower than back to back (75.9 vs
+                                      68.0 us at batch 32), so off by default; see DESIGN.md 4.1 */
 
 const char *genre_b200_last_error(void);
 /* library/ABI version: major*1000 + minor */

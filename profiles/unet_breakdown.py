@@ -31,7 +31,7 @@ if os.environ.get("NCU"):   # kernel list of ONE warm forward: run under `ncu --
 res = {}
 for mode, enabled, tf32 in (("custom", True, True), ("cudnn_tf32", False, True)):
     ops_conv.ENABLED = enabled; torch.backends.cudnn.allow_tf32 = tf32
-    with torch.no_grad():
+    with torch.no_grad(), (ops_conv.precision("tf32") if not enabled else ops_conv.precision(ops_conv.PRECISION)):   # cuDNN column: plain TF32 layers
         for _ in range(3): net(x)
         times.clear()
         for _ in range(5): net(x)
