@@ -320,6 +320,10 @@ def run_b200(args):
     if nets2d == "channels_last":
         net.depth_and_inpaint.net1.to(memory_format=torch.channels_last)
         net.depth_and_inpaint.net2.to(memory_format=torch.channels_last)
+    folded = 0
+    if os.environ.get("GENRE_B200_BENCH_2D_FOLD_BN", "1") != "0":     # eval-mode BatchNorm2d folded into the preceding (transposed) conv
+        folded = compat.fold_batchnorm2d_eval(net.depth_and_inpaint.net1) + compat.fold_batchnorm2d_eval(net.depth_and_inpaint.net2)
+    nets2d += ", %d eval BatchNorm2d folded into their convolutions" % folded
     conv_mode = ops_conv.describe_mode()
 
     def barrier():

@@ -86,3 +86,41 @@ def stub_optional_modules(offline_resnet=True):
                 tvr.resnet18 = resnet18
             except Exception:
                 pass
+
+
+def fold_batchnorm2d_eval(root):
+    """Deployment-side cheap win for the reference's 2D U-ResNets (their code stays the reference's): fold every
+    eval-mode ``BatchNorm2d`` that directly follows a ``Conv2d`` / ``ConvTranspose2d`` into that convolution, in place, on THIS
+    module instance (the BatchNorm becomes ``nn.Identity``).  Patterns: the (conv_k, bn_k) / (deconv_k, bn_k) attribute pairs of
+    torchvision's BasicBlock and networks/revresnet.py's RevBasicBlock / RevBottleneck, and adjacent pairs inside ``nn.Sequential``
+    (stems, down/up-sample branches, the decoders' heads).  Mathematically identical, rounding differs at the 1e-6 level.
+    Returns the number of BatchNorms folded.  Inference only: call after ``.eval()``; state_dict keys of the folded layers change."""
+    import torch.nn as nn
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    folded = 0
+
+    def fuse(conv, bn):
+        return fuse_conv_bn_eval(conv, bn, transpose=isinstance(conv, nn.ConvTranspose2d))
+
+    def ok(conv, bn):
+        return (isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d)) and isinstance(bn, nn.BatchNorm2d) and not bn.training
+                and not conv.training and bn.track_running_stats and conv.out_channels == bn.num_features)
+    for mod in list(root.modules()):
+        if isinstance(mod, nn.Sequential):
+            names = list(mod._modules.keys())
+            for a, b in zip(names, names[1:]):
+                if ok(mod._modules[a], mod._modules[b]):
+                    mod._modules[a] = fuse(mod._modules[a], mod._modules[b])
+                    mod._modules[b] = nn.Identity()
+                    folded += 1
+            continue
+        for k in ("1", "2", "3"):
+            bn = mod._modules.get("bn" + k)
+            for cname in ("conv" + k, "deconv" + k):
+                conv = mod._modules.get(cname)
+                if conv is not None and bn is not None and ok(conv, bn):
+                    mod._modules[cname] = fuse(conv, bn)
+                    mod._modules["bn" + k] = nn.Identity()
+                    folded += 1
+                    break
+    return folded

@@ -83,6 +83,30 @@ def test_genre_net_builds_with_reference_constructor(ref_root):
     assert any(k.startswith("depth_and_inpaint.render_spherical.") or "depth_weight" in k for k in keys)
 
 
+@needs_ref
+def test_fold_batchnorm2d_eval_keeps_the_2d_nets_outputs(ref_root):
+    """compat.fold_batchnorm2d_eval (the 2D nets' cheap win used by bench.py): every BatchNorm2d of the reference's U-ResNets
+    disappears into its convolution and the outputs move only at rounding level"""
+    import models.genre_full_model as gfm
+    from genre_shapehd_b200.synth_genre import init_genre_net_for_bench
+    torch.manual_seed(0)
+    net = gfm.Net(genre_opt(), gfm.Model)
+    init_genre_net_for_bench(net)
+    net.eval()
+    dn = net.depth_and_inpaint
+    x = types.SimpleNamespace(rgb=torch.randn(1, 3, 256, 256))      # the min/max head needs the 8x8 encoder output of a 256^2 image
+    s = torch.rand(1, 1, 160, 160)
+    with torch.no_grad():
+        a1, a2 = dn.net1(x), dn.net2(s)
+        n = compat.fold_batchnorm2d_eval(dn.net1) + compat.fold_batchnorm2d_eval(dn.net2)
+        b1, b2 = dn.net1(x), dn.net2(s)
+    assert n == 124 and not any(isinstance(m, torch.nn.BatchNorm2d) for m in list(dn.net1.modules()) + list(dn.net2.modules()))
+    for a, b in ((a1, b1), (a2, b2)):
+        for k in a:
+            assert (a[k] - b[k]).abs().max().item() <= 1e-5 * max(1.0, a[k].abs().max().item()), k
+    assert compat.fold_batchnorm2d_eval(dn.net1) == 0            # idempotent
+
+
 # ---- on the GPU: the frozen callers RUN on the drop-in -----------------------------------------------------------------
 def genre_inputs(batch, device, seed=0):
     """C3 inputs: rgb ~ N(0,1), silhou = 100 * disc mask (scale_25d, marrnetbase.py:17)"""
