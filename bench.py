@@ -442,7 +442,7 @@ def run_b200(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (3D convolutions: %s)" % conv_mode, "data": "synthetic",
+                "dtype": "f32", "data": "synthetic",
                 "config": config(args, world, {"conv_mode": conv_mode, "nets2d": "reference uresnet.py modules on cuDNN (TF32 allowed, PyTorch default), %s" % nets2d}),
                 "e2e": e2e, "gpu_launches": own_per_step * K,
                 "launch_mode": "cuda_graph" if use_graph else "python" + ("; " + graph_note if graph_note else ""),
