@@ -1,4 +1,5 @@
 #!/bin/bash
+# bench.py on N GPUs of one box:  gpurun --gpus N -- 'NGPU=N bash profiles/r02_multi_gpu.sh'  -> gpurun_out/r02/bench_nN.json
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/r02; mkdir -p $O
 N=${NGPU:-2}
