@@ -599,14 +599,14 @@ static bool make_halo_tmap(CUtensorMap *m, const void *base, long long planes, i
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// GENRE_B200_CONV_TMA=0 keeps the cp.async halo producer
+// halo producer: tensor copies (default) or the cp.async path (GENRE_B200_CONV_TMA=0, or genre_b200_conv_set_tma(0))
+static int g_conv_tma = -1;
 static bool conv_use_tma() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_conv_tma < 0) {
     const char *e = getenv("GENRE_B200_CONV_TMA");
-    v = (e && e[0] == '0') ? 0 : 1;
+    g_conv_tma = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1 && tmap_encoder() != nullptr;
+  return g_conv_tma == 1 && tmap_encoder() != nullptr;
 }
 
 template <int TZ, int T, int NPAD, int MT, int MODE, int OP, bool TMA>
@@ -687,6 +687,14 @@ static int launch_conv_merged8(const ConvTParams &p, cudaStream_t st) {
 }  // namespace gb
 
 using namespace gb;
+
+// Select the halo producer of the convolution kernels: 1 = cp.async.bulk.tensor (TMA, default), 0 = 16-byte cp.async by 128
+// threads.  Returns the previous setting.  Process-wide; meant for A/B timing and for testing both producers in one process.
+extern "C" int genre_b200_conv_set_tma(int enable) {
+  const int prev = conv_use_tma() ? 1 : 0;
+  g_conv_tma = enable ? 1 : 0;
+  return prev;
+}
 
 // ConvTranspose3d(kernel K in {4, 8}, stride 2, padding K/2 - 1) forward on channel-blocked activations.
 //   src0 [B*D][cg0][H][W][4], src1 [B*D][cg1][H][W][4] or NULL: the two halves of the channel concatenation

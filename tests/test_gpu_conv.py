@@ -575,3 +575,25 @@ def test_direct_hi_lo_conversions_equal_convert_then_split():
     x4 = torch.randn(2, 2, 8, 4, 12, device=DEV)
     assert torch.equal(ops_conv.space_to_depth4_blocked(x4, 16, torch.float16),
                        ops_conv._split2(ops_conv.space_to_depth4_blocked(x4, 4, None)))
+
+
+def test_both_halo_producers_give_identical_results():
+    """the TMA producer (cp.async.bulk.tensor, zero-filled out-of-range box elements) and the cp.async producer feed the same MMAs:
+    bit-identical outputs, in one process (genre_b200_conv_set_tma)"""
+    from genre_shapehd_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(8)
+    m = nets.ConvTranspose3d(80, 20, 8, 2, 3).to(DEV)
+    blk = nets.Conv3d(64, 128, 4, 2, 1).to(DEV)
+    x = torch.randn(2, 80, 3, 32, 32, device=DEV)
+    xc = torch.randn(1, 64, 4, 32, 32, device=DEV)
+    prev = lib.genre_b200_conv_set_tma(1)
+    try:
+        with torch.no_grad():
+            a, ac = ops_conv.conv_transpose3d(x, m), ops_conv.conv3d(xc, blk)
+            lib.genre_b200_conv_set_tma(0)
+            b, bc = ops_conv.conv_transpose3d(x, m), ops_conv.conv3d(xc, blk)
+    finally:
+        lib.genre_b200_conv_set_tma(prev)
+    assert a is not None and ac is not None
+    assert torch.equal(a, b) and torch.equal(ac, bc)
