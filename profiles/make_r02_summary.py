@@ -122,7 +122,8 @@ def main():
     for n in ("pytest_gpu.txt", "bench_n1.json", "bench_reference_arm.json", "unet_breakdown_exact.json", "unet_breakdown_f16.json",
               "microbench_ops.json", "microbench_render.json", "microbench_cam_bp.json", "genre_breakdown.json", "train_unet_exact.json",
               "train_unet_f16.json", "train_unet_launches_f16.csv", "launches_genre_step.csv", "unet_tensor_pipe_exact.csv",
-              "unet_tensor_pipe_f16.csv", "bench_n2.json", "bench_n8.json", "bench_n4.json"):
+              "unet_tensor_pipe_f16.csv", "bench_n2.json", "bench_n8.json", "bench_n4.json", "train_shapehd_launches.csv",
+              "train_wgan_launches.csv", "train_genre_launches.csv"):
         copy(n)
     b, r = load_json("bench_n1.json"), load_json("bench_reference_arm.json")
     if b:
@@ -164,6 +165,10 @@ def main():
     md.append("\n## Unet_3D training step B=4, opt-in f16 mode (`r02_train_unet_launches_f16.csv`)\n")
     t, tot = launch_table("train_unet_launches_f16.csv", 16)
     md.append(t)
+    for w, title in (("shapehd", "ShapeHD fine-tune step, B=8"), ("wgan", "WGAN-GP critic step, B=8"), ("genre", "GenRe joint fine-tune + Chamfer step, B=4")):
+        md.append("\n## %s, default (exact) conv mode (`r02_train_%s_launches.csv`)\n" % (title, w))
+        t, _ = launch_table("train_%s_launches.csv" % w, 12)
+        md.append(t)
     tp = {}
     for mode in ("exact", "f16"):
         x = tensor_pipe("unet_tensor_pipe_%s.csv" % mode)
