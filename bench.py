@@ -373,6 +373,10 @@ def run_b200(args):
         time.sleep(0.25)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("GENRE_B200_BENCH_PROFILE_RANGE") == "1"    # `ncu --profile-from-start off`: the timed steps only
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     t_wall0 = time.time()
     e0.record()
     for i in range(K):
@@ -380,6 +384,9 @@ def run_b200(args):
     e1.record()
     barrier()
     t_wall1 = time.time()
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     t_load1 = t_wall1
     try:    # keep the same step running (untimed) so that nvidia-smi's 100 ms samples describe this kernel mix under load

@@ -36,7 +36,11 @@ ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
 #   conv_k8s2_wgrad  Unet_3D.enc1's weight gradient (first-order backward only; double backward stays on aten)
 #   conv_k4s2_s2d    Conv3d(1 or 2 -> 64, k4 s2) as 3 taps over the 2x space-to-depth input (VoxelDiscriminator main.0:
 #                    cuDNN 2.6 ms in eval at B=16 and a 35 ms kernel per call in the WGAN-GP step at B=8)
-_all_policy = {"conv_k4s2_s2d", "conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
+#   flat          the k4 s2 convolutions of the small volumes (coarse side <= 8^3: Unet_3D.enc4, enc5, dec2, dec3 and the 4^3 / 8^3
+#                 stages of the ShapeHD nets) on the flattened-volume kernel (csrc/convflat.cu); fp16 / f16x2 modes, inference
+#   skinny        Conv3d whose kernel covers its whole input (Unet_3D.enc6) / ConvTranspose3d on a 1^3 input (dec1, the decoders'
+#                 first layer) in eval mode as weight-streaming FP32 products (csrc/skinny_gemm.cu); every precision mode (exact fp32)
+_all_policy = {"skinny", "flat", "conv_k4s2_s2d", "conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
 _default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
@@ -798,6 +802,167 @@ def _conv_k4s2(x, m, bn, slope):
     return from_blocked(out, b, cout)
 
 
+# ---- small volumes: the flattened, zero-separated implicit GEMM (csrc/convflat.cu) ------------------------------------------
+FLAT_MAX = 8      # coarse-side extent routed to the flat kernel (larger planes belong to the halo kernels of csrc/convt3d.cu)
+
+
+def flat_npad(cout):
+    """accumulator tile width: the one of {64, 80} that pads Cout least (80 on a tie: fewer N tiles)"""
+    return 64 if -(-cout // 64) * 64 < -(-cout // 80) * 80 else 80
+
+
+def flat_shifts(h, w, transposed):
+    """[8 groups][8 taps] position shifts of csrc/convflat.cu (group = output parity class of a transposed conv, or input
+    sub-volume of a strided conv; tap t = (tz,ty,tx); bit 2 = z) in a volume whose rows / planes are w+1 / (h+1)(w+1) positions"""
+    table = []
+    for g in range(8):
+        row = []
+        for t in range(8):
+            d = []
+            for k in range(3):
+                par, tt = (g >> (2 - k)) & 1, (t >> (2 - k)) & 1
+                d.append(((1 - tt) if par else -tt) if transposed else 1 - par - tt)
+            row.append(d[0] * (h + 1) * (w + 1) + d[1] * (w + 1) + d[2])
+        table.append(row)
+    return table
+
+
+def pack_flat_convt_weights(weight, npad, group=8):
+    """ConvTranspose3d weight [Cin, Cout, 4, 4, 4] (stride 2, padding 1) ->
+    [8 class][ntile][ceil(Cin/16) K step][8 taps][2 kcore][npad/8][8 n][8 k]: class parity p, tap t reads the input at shift
+    d = (1 - t if p else -t), kernel index k = p + 1 - 2 d, per dimension."""
+    cin, cout = weight.shape[0], weight.shape[1]
+    cpad, nt = -(-cin // 16) * 16, -(-cout // npad)
+    weq = weight.new_zeros((8, 8, cpad, nt * npad))                               # (class, tap, ci, n)
+
+    def kidx(par, t):
+        return par + 1 - 2 * ((1 - t) if par else -t)
+    for cls in range(8):
+        for tap in range(8):
+            kz, ky, kx = (kidx((cls >> (2 - k)) & 1, (tap >> (2 - k)) & 1) for k in range(3))
+            weq[cls, tap, :cin, :cout] = weight[:, :, kz, ky, kx]
+    sub = weq.reshape(8, 8, cpad // 16, 2, 8, nt, npad // 8, 8)                   # (class, tap, kc, kk, e, ntile, ng, r)
+    return _finish_pack(sub.permute(0, 5, 2, 1, 3, 6, 7, 4).contiguous(), group)  # (class, ntile, kc, tap, kk, ng, r, e)
+
+
+def pack_flat_conv_weights(weight, npad, group=8):
+    """Conv3d weight [Cout, Cin, 4, 4, 4] (stride 2, padding 1, Cin % 16 == 0) -> [1][ntile][8*Cin/16 K step][8 taps][2][npad/8][8][8]:
+    K = the 8 parity sub-volumes of the input, sub-volume parity p and tap t use kernel index 3 - 2t - p (shift 1 - p - t)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    nt = -(-cout // npad)
+    weq = weight.new_zeros((8, 8, cin, nt * npad))                                # (tap, sub-volume, ci, n)
+    for sv in range(8):
+        for tap in range(8):
+            kz, ky, kx = (3 - 2 * ((tap >> (2 - k)) & 1) - ((sv >> (2 - k)) & 1) for k in range(3))
+            weq[tap, sv, :, :cout] = weight[:, :, kz, ky, kx].t()
+    sub = weq.reshape(8, 8 * cin // 16, 2, 8, nt, npad // 8, 8)                   # (tap, kc, kk, e, ntile, ng, r)
+    return _finish_pack(sub.permute(4, 1, 0, 2, 5, 6, 3).contiguous().unsqueeze(0), group)
+
+
+def _flat_common(m):
+    return ("flat" in POLICY and ENABLED and (_f16() or _x2()) and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
+            and tuple(m.padding) == (1, 1, 1) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1)
+
+
+def _flat_source_ok(x):
+    return torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[1] % 8 == 0
+
+
+def _flat_convt_supported(sources, m):
+    return (isinstance(m, torch.nn.ConvTranspose3d) and _flat_common(m) and tuple(m.output_padding) == (0, 0, 0)
+            and all(_flat_source_ok(x) and x.shape[2:] == sources[0].shape[2:] and x.shape[0] == sources[0].shape[0] for x in sources)
+            and max(sources[0].shape[2:]) <= FLAT_MAX and sum(x.shape[1] for x in sources) == m.in_channels
+            and _no_autograd(*sources, m.weight, m.bias))
+
+
+def _flat_conv_supported(x, m):
+    return (isinstance(m, torch.nn.Conv3d) and _flat_common(m) and m.padding_mode == "zeros" and _flat_source_ok(x)
+            and x.shape[1] % 16 == 0 and x.shape[1] == m.in_channels and all(v % 2 == 0 for v in x.shape[2:])
+            and max(x.shape[2:]) <= 2 * FLAT_MAX and _no_autograd(x, m.weight, m.bias))
+
+
+def _flat_run(sources, m, bn, slope, transposed):
+    cout = m.out_channels
+    npad = flat_npad(cout)
+    dev = sources[0].device
+    aff = _affine(m, bn, -(-cout // npad) * npad, dev)
+    if aff is None:
+        return None
+    b = sources[0].shape[0]
+    if transposed:
+        d, h, w = sources[0].shape[2:]
+        groups = sum(x.shape[1] for x in sources) // 8
+        wpack = _pack(m, ("flat_convt", npad, 8), lambda wt: pack_flat_convt_weights(wt, npad), 2)
+    else:
+        d, h, w = (v // 2 for v in sources[0].shape[2:])
+        groups = sources[0].shape[1]
+        wpack = _pack(m, ("flat_conv", npad, 8), lambda wt: pack_flat_conv_weights(wt, npad), 2)
+    cgs = groups + (groups & 1)
+    parts = _parts()
+    positions = _lib.load().genre_b200_convflat_positions(b, d, h, w, None)
+    operand = torch.empty((parts, cgs, positions, 8), device=dev, dtype=torch.float16)
+    st = _lib.stream_ptr(sources[0])
+    off = 0
+    for x in sources:
+        x = x.contiguous()
+        _lib.call("genre_b200_convflat_pack", x.data_ptr(), x.shape[1], b, d, h, w, 0 if transposed else 1, operand.data_ptr(), off, cgs,
+                  parts, 0, st)
+        off += x.shape[1] // 8 if transposed else x.shape[1]
+    if off < cgs:
+        _lib.call("genre_b200_convflat_pack", None, 0, b, d, h, w, 0, operand.data_ptr(), off, cgs, parts, cgs - off, st)
+    od, oh, ow = (2 * d, 2 * h, 2 * w) if transposed else (d, h, w)
+    out = torch.empty((b, cout, od, oh, ow), device=dev, dtype=torch.float32)
+    _lib.call("genre_b200_convflat_forward", operand.data_ptr(), cgs, b, d, h, w, 1 if transposed else 0, wpack.data_ptr(), npad,
+              _op_flag(), aff[0].data_ptr(), aff[1].data_ptr(), 1.0 if slope is None else float(slope), out.data_ptr(), cout, st)
+    return out
+
+
+# ---- the 1^3 end of the U-Net: weight-streaming FP32 products (csrc/skinny_gemm.cu) ------------------------------------------
+def _skinny_ok(x, m):
+    return ("skinny" in POLICY and ENABLED and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+            and m.groups == 1 and tuple(m.dilation) == (1, 1, 1) and tuple(m.padding) == (0, 0, 0) and m.weight.dtype == torch.float32
+            and not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, m.weight, m.bias))))
+
+
+def _skinny_conv_supported(x, m):
+    """Conv3d whose kernel is its whole input: one output voxel per (sample, channel)"""
+    return (isinstance(m, torch.nn.Conv3d) and _skinny_ok(x, m) and m.padding_mode == "zeros" and tuple(x.shape[2:]) == tuple(m.kernel_size)
+            and x.shape[1] == m.in_channels and (x.shape[1] * x.shape[2] * x.shape[3] * x.shape[4]) % 4 == 0)
+
+
+def _skinny_convt_supported(x, m):
+    """ConvTranspose3d of a 1^3 input: the output is the kernel weighted by the input channels"""
+    return (isinstance(m, torch.nn.ConvTranspose3d) and _skinny_ok(x, m) and tuple(x.shape[2:]) == (1, 1, 1) and x.shape[1] == m.in_channels
+            and tuple(m.output_padding) == (0, 0, 0) and (m.out_channels * m.kernel_size[0] * m.kernel_size[1] * m.kernel_size[2]) % 4 == 0)
+
+
+def _aligned(t):
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def _skinny_run(x, m, bn, slope, transposed):
+    cout = m.out_channels
+    aff = _affine(m, bn, cout, x.device)
+    if aff is None:
+        return None
+    b = x.shape[0]
+    x2 = _aligned(x.reshape(b, -1))
+    w = _aligned(m.weight.detach())
+    k = x2.shape[1]
+    if transposed:
+        kvol = m.kernel_size[0] * m.kernel_size[1] * m.kernel_size[2]
+        n, div, shape = cout * kvol, kvol, (b, cout) + tuple(m.kernel_size)
+    else:
+        n, div, shape = cout, 1, (b, cout, 1, 1, 1)
+    nbytes = _lib.load().genre_b200_skinny_gemm_workspace_bytes(b, n, k, 0 if transposed else 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    _lib.call("genre_b200_skinny_gemm", x2.data_ptr(), w.data_ptr(), b, n, k, 0 if transposed else 1, div, aff[0].data_ptr(),
+              aff[1].data_ptr(), 1.0 if slope is None else float(slope), out.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr(x))
+    return out
+
+
 def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -1027,6 +1192,10 @@ def conv3d(x, m, bn=None, slope=None):
         return _train_forward(x, m, _conv_k4s2_supported(x, m) or _conv_k8s2_supported(x, m) or _conv_k4s2_s2d_supported(x, m))
     if not _no_autograd(x, m.weight, m.bias):
         return None
+    if _skinny_conv_supported(x, m):
+        return _skinny_run(x, m, bn, slope, False)
+    if _flat_conv_supported(x, m):
+        return _flat_run((x,), m, bn, slope, False)
     if _conv_k4s2_supported(x, m):
         return _conv_k4s2(x, m, bn, slope)
     if _conv_k4s2_s2d_supported(x, m):
@@ -1178,6 +1347,10 @@ def conv_transpose3d(x, m, bn=None, slope=None):
         y = convt_c1_tc((x,), m)
         if y is not None:
             return y
+    if not isinstance(x, BlockedActivation) and _skinny_convt_supported(x, m):
+        return _skinny_run(x, m, bn, slope, True)
+    if not isinstance(x, BlockedActivation) and _flat_convt_supported((x,), m):
+        return _flat_run((x,), m, bn, slope, True)
     if (bn is None and slope is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
             and _convt_c1_supported(x.shape[1], x.shape[2:], m, (x,)) and _no_autograd(x, m.weight, m.bias)):
         return convt_c1(_blocked_f32(x), None, x.shape[0], m)
@@ -1295,6 +1468,12 @@ def deconv_skip(x, skip, conv, bn=None, slope=None, keep_blocked=False):
         return convt_c1(_blocked_f32(x), _blocked_f32(skip), x.shape[0], conv)
     if isinstance(x, BlockedActivation):
         x = x.ncdhw()
+    if (torch.is_tensor(skip) and skip.dim() == 5 and tuple(skip.shape[2:]) == (1, 1, 1) and torch.is_tensor(x) and x.dim() == 5
+            and tuple(x.shape[2:]) == (1, 1, 1)):
+        xc = torch.cat((x, skip), dim=1)
+        return _skinny_run(xc, conv, bn, slope, True) if _skinny_convt_supported(xc, conv) else None
+    if _flat_convt_supported((x, skip), conv):
+        return _flat_run((x, skip), conv, bn, slope, True)
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]
             and x.shape[1] % _group() == 0 and skip.shape[1] % _group() == 0
             and _convt_supported((x.shape[0], x.shape[1] + skip.shape[1]) + tuple(x.shape[2:]), conv)

@@ -214,6 +214,37 @@ int genre_b200_conv3d_k4s2_forward(const void *src, int cgs, int kblocks, int64_
                                    const float *scale, const float *shift, float slope,
                                    float *out, int cgo, void *stream);
 
+/* The k 4 / s 2 / p 1 convolutions of the SMALL volumes (coarse side <= 8^3: Unet_3D.enc4, enc5, dec2, dec3,
+ * networks/networks.py:157-165; the 4^3 / 8^3 stages of VoxelDecoder / VoxelGenerator / VoxelDiscriminator :40-57,:79-97,:247-256)
+ * as a tcgen05 implicit GEMM over the flattened, zero-separated volume (csrc/convflat.cu).  Replaces the cuDNN calls behind
+ * those nn.Conv3d / nn.ConvTranspose3d modules in eval mode.
+ *   genre_b200_convflat_positions: positions per channel-group array of the operand of a coarse (B, D, H, W) volume
+ *       (*lead = index of position 0);
+ *   genre_b200_convflat_pack: NCDHW fp32 -> operand [parts][cgs][P][8 fp16] (parts 2 = fp16 hi | lo' = (a - hi) * 2^11), groups
+ *       [cg_off, ...); subvol = 1: src is [B, C, 2D, 2H, 2W] and becomes 8 parity sub-volume blocks of C/8 groups (C % 8 == 0);
+ *       src NULL: zero `zero_groups` groups (padding to an even group count);
+ *   genre_b200_convflat_forward: out[B, Cout, Do, Ho, Wo] (NCDHW fp32) = lrelu(scale * conv + shift); transposed 1:
+ *       ConvTranspose3d, output 2x the coarse volume; 0: Conv3d of the 2x volume given as sub-volume blocks (cgs % 16 == 0),
+ *       output the coarse volume.  wpack [classes 8|1][ceil(Cout/npad)][cgs/2][8 taps][2][parts*npad/8][8][8] fp16, npad 64 | 80,
+ *       op 1 (fp16 operands) | 2 (hi/lo split, fp32-accurate). */
+int64_t genre_b200_convflat_positions(int64_t B, int D, int H, int W, int *lead);
+int genre_b200_convflat_pack(const float *src, int C, int64_t B, int D, int H, int W, int subvol, void *operand, int cg_off,
+                             int cgs, int parts, int zero_groups, void *stream);
+int genre_b200_convflat_forward(const void *operand, int cgs, int64_t B, int D, int H, int W, int transposed,
+                                const void *wpack, int npad, int op, const float *scale, const float *shift, float slope,
+                                float *out, int Cout, void *stream);
+
+/* The two degenerate convolutions at the bottom of the U-Net as weight-streaming FP32 products (csrc/skinny_gemm.cu):
+ * Conv3d whose kernel covers its whole input (Unet_3D.enc6, networks/networks.py:157: W is [N = Cout][K = Cin*k^3], w_is_nk = 1)
+ * and ConvTranspose3d on a 1^3 input (Unet_3D.dec1 :162, VoxelDecoder / VoxelGenerator main.0 :40,:79: W is [K = Cin][N = Cout*k^3],
+ * w_is_nk = 0, chan_div = k^3).  Replaces the cuDNN / cuBLAS calls behind those modules in eval mode.
+ *   out[M][N] = lrelu(scale[n / chan_div] * (x[M][K] @ W) + shift[n / chan_div]); fp32 throughout (FP32 FMAs, fixed summation order);
+ *   the contiguous extent of W a multiple of 4; workspace = genre_b200_skinny_gemm_workspace_bytes(M, N, K, w_is_nk). */
+size_t genre_b200_skinny_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int w_is_nk);
+int genre_b200_skinny_gemm(const float *x, const float *W, int64_t M, int64_t N, int64_t K, int w_is_nk, int chan_div,
+                           const float *scale, const float *shift, float slope, float *out, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
 /* ConvTranspose3d(Cin -> 1, kernel 4, stride 2, padding 1) forward on channel-blocked fp32 inputs (FP32 pipe: with one
  * output channel there is no GEMM for the tensor cores).  Replaces the cuDNN call behind the last layer of each decoder:
  * Unet_3D.dec6 (networks/networks.py:167-168, two sources = the skip concatenation), VoxelDecoder main.17 (:57),

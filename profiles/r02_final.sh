@@ -8,8 +8,8 @@ python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -15 > $O/pytest_gpu.txt
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_n1.json 2> $O/bench_n1.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --cpu-budget 90 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 # launch list of the headline step (eager launches so that every kernel is a separate record)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches_genre_step.csv \
-    python bench.py --steps 2 --warmup 1 --no-graph --skip cpu,ddp,e2e,secondary,roofline > $O/bench_under_ncu.log 2>&1
+GENRE_B200_BENCH_PROFILE_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $O/launches_genre_step.csv python bench.py --steps 1 --warmup 3 --no-graph --skip cpu,ddp,e2e,secondary,roofline > $O/bench_under_ncu.log 2>&1
 # tensor-pipe activity of every conv kernel of one Unet_3D forward, default (exact) mode and the opt-in fp16 mode
 for mode in exact f16; do
   GENRE_B200_CONV_PRECISION=$mode NCU=1 ncu --profile-from-start off --clock-control none \

@@ -148,7 +148,7 @@ def test_autograd_and_unsupported_shapes_fall_back(monkeypatch):
     y.sum().backward()
     assert x.grad is not None
     with torch.no_grad():
-        assert ops_conv.conv_transpose3d(torch.randn(1, 16, 2, 8, 8, device=DEV), m) is None   # W=8 not covered
+        assert ops_conv.conv_transpose3d(torch.randn(1, 16, 2, 12, 12, device=DEV), m) is None   # W=12: no kernel
 
 
 @pytest.mark.parametrize("cin,cout,b,d,h,w", [(2, 20, 1, 4, 32, 32), (2, 20, 2, 8, 64, 64), (4, 12, 1, 6, 32, 128),
