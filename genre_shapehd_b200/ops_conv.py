@@ -803,7 +803,7 @@ def _conv_k4s2(x, m, bn, slope):
 
 
 # ---- small volumes: the flattened, zero-separated implicit GEMM (csrc/convflat.cu) ------------------------------------------
-FLAT_MAX = 8      # coarse-side extent routed to the flat kernel (larger planes belong to the halo kernels of csrc/convt3d.cu)
+FLAT_MAX = int(os.environ.get("GENRE_B200_CONV_FLAT_MAX", "8"))      # coarse-side extent routed to the flat kernel (larger planes belong to the halo kernels of csrc/convt3d.cu)
 
 
 def flat_npad(cout):
@@ -861,7 +861,8 @@ def pack_flat_conv_weights(weight, npad, group=8):
 
 def _flat_common(m):
     return ("flat" in POLICY and ENABLED and (_f16() or _x2()) and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
-            and tuple(m.padding) == (1, 1, 1) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1)
+            and tuple(m.padding) == (1, 1, 1) and tuple(m.dilation) == (1, 1, 1) and m.groups == 1
+            and m.out_channels >= 8)     # fewer output channels: the one-channel kernels (an N tile here is 64 columns)
 
 
 def _flat_source_ok(x):
