@@ -52,6 +52,7 @@ _SIGNATURES = {
     "genre_b200_blocked_f32_to_f16": [_ptr, _int, _i64, _i64, _i64, _ptr, _ptr],
     "genre_b200_blocked_split2_f16": [_ptr, _int, _i64, _i64, _i64, _ptr, _ptr],
     "genre_b200_voxel_surface": [_ptr, _i64, _int, _int, _int, _ptr, _ptr, _size, _ptr],
+    "genre_b200_convt_c1_col2im_forward": [_ptr, _int, _ptr, _int, _i64, _i64, _i64, _i64, _ptr, _int, _ptr, _ptr, _ptr],
     "genre_b200_skinny_gemm": [_ptr, _ptr, _i64, _i64, _i64, _int, _int, _ptr, _ptr, _f32, _ptr, _ptr, _size, _ptr],
     "genre_b200_convflat_pack": [_ptr, _int, _i64, _int, _int, _int, _int, _ptr, _int, _int, _int, _int, _ptr],
     "genre_b200_convflat_forward": [_ptr, _int, _i64, _int, _int, _int, _int, _ptr, _int, _int, _ptr, _ptr, _f32, _ptr, _int, _ptr],
@@ -96,7 +97,7 @@ _LAUNCHES = {
     "genre_b200_convt_c1_forward": 1, "genre_b200_conv3d_k4s2_forward": 1,
     "genre_b200_render_spherical_forward_pre": 1, "genre_b200_render_spherical_forward_skip": 2, "genre_b200_sph_bp_forward_fused": 2, "genre_b200_scale_clamp_strided": 1,
     "genre_b200_bn_act_train_forward": 3, "genre_b200_bn_act_train_backward": 2, "genre_b200_conv_k8s2_wgrad": 2, "genre_b200_convt_c1_wgrad": 2, "genre_b200_convt_c1_dgrad": 1,
-    "genre_b200_blocked_split3": 1, "genre_b200_blocked_split2_f16": 1, "genre_b200_voxel_surface": 2, "genre_b200_skinny_gemm": 2, "genre_b200_convflat_pack": 1, "genre_b200_convflat_forward": 1, "genre_b200_convt_c1_tc_forward": 1, "genre_b200_blocked_f32_to_f16": 1,
+    "genre_b200_blocked_split3": 1, "genre_b200_blocked_split2_f16": 1, "genre_b200_voxel_surface": 2, "genre_b200_convt_c1_col2im_forward": 1, "genre_b200_skinny_gemm": 2, "genre_b200_convflat_pack": 1, "genre_b200_convflat_forward": 1, "genre_b200_convt_c1_tc_forward": 1, "genre_b200_blocked_f32_to_f16": 1,
     "genre_b200_convt3d_s2_merged_forward": 1, "genre_b200_conv3d_k8s2_s4d_forward": 1, "genre_b200_ncdhw_to_blocked": 1, "genre_b200_blocked_to_ncdhw": 1,
 }
 

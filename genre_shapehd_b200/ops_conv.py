@@ -40,7 +40,9 @@ ENABLED = os.environ.get("GENRE_B200_CONV", "1") != "0"
 #                 stages of the ShapeHD nets) on the flattened-volume kernel (csrc/convflat.cu); fp16 / f16x2 modes, inference
 #   skinny        Conv3d whose kernel covers its whole input (Unet_3D.enc6) / ConvTranspose3d on a 1^3 input (dec1, the decoders'
 #                 first layer) in eval mode as weight-streaming FP32 products (csrc/skinny_gemm.cu); every precision mode (exact fp32)
-_all_policy = {"skinny", "flat", "conv_k4s2_s2d", "conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
+#   convt_c1_col2im  the 1-channel layer on 64-wide volumes as a GEMM over the 64 taps + shared-memory col2im (csrc/convt_c1_col2im.cu):
+#                    Unet_3D.dec6 1.33 ms (FP32 stencil) / 0.67 ms (MODE 4, fp16) -> see profiles/r02_summary.md; fp16 and f16x2 modes
+_all_policy = {"convt_c1_col2im", "skinny", "flat", "conv_k4s2_s2d", "conv_k8s2_wgrad", "convt_c1_train", "convt_k8", "conv_k8s2", "convt_c1", "convt_k4", "conv_k4s2", "convt_c1_convert", "convt_c1_tc", "gemm"}
 _default_policy = set(_all_policy)
 _env = os.environ.get("GENRE_B200_CONV_POLICY", "")
 POLICY = set(_all_policy) if _env in ("", "all") else set(x for x in _env.split(",") if x)
@@ -433,6 +435,25 @@ def pack_convt_c1_tc_weights(weight, segments, group=4):
     sub = weq.reshape(ktot // (2 * g), 2, g, 2, 8, 3, 3, 3)               # (kc, kk, e, ng, r, tz, ty, tx)
     out = sub.permute(5, 0, 6, 7, 1, 3, 4, 2).contiguous()
     return _finish_pack(out, g)
+
+
+def pack_convt_c1_col2im_weights(weight, segments, group=8):
+    """ConvTranspose3d weight [Cin, 1, 4, 4, 4] for csrc/convt_c1_col2im.cu: [K step][2 kcore][8 n-groups][8 n][8 k], the GEMM's
+    N = 64 columns are the taps in phase-major order n = t*8 + r, tap k = 2t + r per dimension (t, r = (z,y,x) bit triples);
+    `segments` = [(real channels, padded channels), ...] of the concatenated sources (padded rows zero)."""
+    ktot = sum(pc for _, pc in segments)
+    assert ktot % 16 == 0
+    weq = weight.new_zeros((ktot, 64))
+    r0 = c0 = 0
+    for real, padded in segments:
+        for n in range(64):
+            t, r = n >> 3, n & 7
+            kz, ky, kx = (2 * ((t >> (2 - i)) & 1) + ((r >> (2 - i)) & 1) for i in range(3))
+            weq[r0:r0 + real, n] = weight[c0:c0 + real, 0, kz, ky, kx]
+        c0, r0 = c0 + real, r0 + padded
+    assert c0 == weight.shape[0]
+    sub = weq.reshape(ktot // 16, 2, 8, 8, 8)                                   # (ks, kk, e, ng, r)
+    return _finish_pack(sub.permute(0, 1, 3, 4, 2).contiguous(), group)         # (ks, kk, ng, r, e)
 
 
 _PLAN_MODE = False    # while True the packers run on an index tensor: no dtype conversion at the end
@@ -1302,6 +1323,38 @@ def convt_c1_tc(inputs, m, sigmoid=False):
     return out
 
 
+def convt_c1_col2im(inputs, m):
+    """ConvTranspose3d(Cin -> 1, k4, s2, p1) over the channel concatenation of `inputs` on 64-wide volumes: tap GEMM + col2im
+    (csrc/convt_c1_col2im.cu); NCDHW [B,1,2D,2H,128] or None if not covered."""
+    x0 = inputs[0]
+    if not ("convt_c1_col2im" in POLICY and ENABLED and (_f16() or _x2()) and tuple(m.kernel_size) == (4, 4, 4) and tuple(m.stride) == (2, 2, 2)
+            and tuple(m.padding) == (1, 1, 1) and tuple(m.output_padding) == (0, 0, 0) and tuple(m.dilation) == (1, 1, 1)
+            and m.groups == 1 and m.out_channels == 1 and len(inputs) <= 2
+            and all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 5 and t.shape[2:] == x0.shape[2:] for t in inputs)
+            and x0.shape[4] == 64 and x0.shape[3] % 8 == 0 and x0.shape[0] <= 65535 and _no_autograd(*inputs, m.weight, m.bias)):
+        return None
+    ops = [_operand_of(t) for t in inputs]
+    if any(o is None for o in ops):
+        return None
+    segments = tuple((t.shape[1], o[1]) for t, o in zip(inputs, ops))
+    if sum(pc for _, pc in segments) % 16 != 0:
+        return None
+    wpack = _pack(m, ("c1_col2im", segments, 8), lambda wt: pack_convt_c1_col2im_weights(wt, segments), 0)
+    b, _, d, h, w = x0.shape
+    if m.bias is not None:
+        bias = m.bias.detach()
+    else:
+        bias = m.__dict__.get("_gb_zero_bias")
+        if bias is None or bias.device != x0.device:
+            bias = m.__dict__["_gb_zero_bias"] = torch.zeros(1, device=x0.device)
+    out = torch.empty((b, 1, 2 * d, 2 * h, 2 * w), device=x0.device, dtype=torch.float32)
+    s1 = ops[1][0] if len(ops) > 1 else None
+    _lib.call("genre_b200_convt_c1_col2im_forward", ops[0][0].data_ptr(), ops[0][0].shape[1] // _parts(), s1.data_ptr() if s1 is not None else None,
+              s1.shape[1] // _parts() if s1 is not None else 0, b, d, h, w, wpack.data_ptr(), _op_flag(), bias.data_ptr(), out.data_ptr(),
+              _lib.stream_ptr(out))
+    return out
+
+
 def _has_blocked(x):
     return _cached_blocked(x) is not None
 
@@ -1345,7 +1398,9 @@ def conv_transpose3d(x, m, bn=None, slope=None):
             return _ConvTC1Train.apply(x, m.weight, m.bias, m)
         return _train_forward(x, m, m.out_channels > 1 and _convt_supported(x.shape, m))
     if bn is None and slope is None and m.out_channels == 1:
-        y = convt_c1_tc((x,), m)
+        y = convt_c1_col2im((x,), m)
+        if y is None:
+            y = convt_c1_tc((x,), m)
         if y is not None:
             return y
     if not isinstance(x, BlockedActivation) and _skinny_convt_supported(x, m):
@@ -1459,7 +1514,9 @@ def deconv_skip(x, skip, conv, bn=None, slope=None, keep_blocked=False):
     """cat(x, skip) -> ConvTranspose3d [-> eval-mode BatchNorm3d folded into the epilogue -> LeakyReLU(slope)] with the
     concatenation walked as two K ranges instead of being materialised.  None if not covered."""
     if bn is None and conv.out_channels == 1:
-        y = convt_c1_tc((x, skip), conv)
+        y = convt_c1_col2im((x, skip), conv)
+        if y is None:
+            y = convt_c1_tc((x, skip), conv)
         if y is not None:
             return y
     if (bn is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and skip.shape[2:] == x.shape[2:]

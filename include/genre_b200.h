@@ -245,6 +245,15 @@ int genre_b200_skinny_gemm(const float *x, const float *W, int64_t M, int64_t N,
                            const float *scale, const float *shift, float slope, float *out, void *workspace,
                            size_t workspace_bytes, void *stream);
 
+/* ConvTranspose3d(Cin -> 1, kernel 4, stride 2, padding 1) on 64-wide volumes as a tcgen05 GEMM over the 64 kernel taps
+ * (P[position, tap] = sum_c x[c, position] W[c, tap]) followed by a shared-memory col2im (csrc/convt_c1_col2im.cu).  Replaces the
+ * cuDNN call behind the last layer of each decoder (Unet_3D.dec6 networks/networks.py:167-168, VoxelDecoder :57, VoxelGenerator :98).
+ *   src0 [B*D][parts*cg0][H][64][8 fp16], src1 likewise (cg1 groups) or NULL; parts 1 (op 1: fp16) | 2 (op 2: hi | lo' split,
+ *   fp32-accurate); cg0 + cg1 even; H % 8 == 0; W == 64; wpack [(cg0+cg1)/2][2][parts*8][8][8] fp16 with row n = t*8 + r = tap 2t + r
+ *   per dimension; bias: one float on the device; out [B][2D][2H][128] fp32, fully overwritten (a strided memset node + one kernel). */
+int genre_b200_convt_c1_col2im_forward(const void *src0, int cg0, const void *src1, int cg1, int64_t B, int64_t D, int64_t H,
+                                       int64_t W, const void *wpack, int op, const float *bias, float *out, void *stream);
+
 /* ConvTranspose3d(Cin -> 1, kernel 4, stride 2, padding 1) forward on channel-blocked fp32 inputs (FP32 pipe: with one
  * output channel there is no GEMM for the tensor cores).  Replaces the cuDNN call behind the last layer of each decoder:
  * Unet_3D.dec6 (networks/networks.py:167-168, two sources = the skip concatenation), VoxelDecoder main.17 (:57),

@@ -171,3 +171,23 @@ def test_skinny_one_voxel_transposed_conv_vs_torch(cin, cout, b, k):
             ref_plain = blk.net[0](torch.cat((x, s), 1))
     assert y.shape == ref.shape and (y - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
     assert plain is not None and (plain - ref_plain).abs().max().item() <= 2e-5 * ref_plain.abs().max().item()
+
+
+@pytest.mark.parametrize("chans,b,d,h", [((32,), 1, 2, 8), ((20, 20), 2, 3, 16), ((64,), 1, 4, 64), ((16, 12), 3, 5, 24), ((40,), 2, 1, 16)])
+def test_convt_one_channel_tap_gemm_col2im_vs_torch(chans, b, d, h):
+    """Unet_3D.dec6's shape class (networks/networks.py:167-168) on csrc/convt_c1_col2im.cu: bands of 8 rows sweeping z, the
+    rows two bands share accumulated with red.add onto the memset's zeros"""
+    torch.manual_seed(sum(chans) + d + h)
+    m = nets.ConvTranspose3d(sum(chans), 1, 4, 2, 1).to(DEV)
+    inputs = tuple(torch.randn(b, c, d, h, 64, device=DEV) for c in chans)
+    with torch.no_grad():
+        y = ops_conv.convt_c1_col2im(inputs, m)
+        again = ops_conv.convt_c1_col2im(inputs, m)
+        routed = ops_conv.conv_transpose3d(inputs[0], m) if len(inputs) == 1 else ops_conv.deconv_skip(inputs[0], inputs[1], m)
+        with fp32_reference():
+            ref = F.conv_transpose3d(torch.cat(inputs, 1), m.weight, m.bias, stride=2, padding=1)
+    assert y is not None and y.shape == ref.shape
+    err, scale = (y - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= _tol() * max(1.0, scale), "max err %g vs scale %g" % (err, scale)
+    assert torch.equal(y, again), "two contributions per shared row, added onto zeros: the result must not depend on CTA order"
+    assert routed is not None and torch.equal(routed, y)
