@@ -81,7 +81,7 @@ EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + [
     "genre_b200_last_error", "genre_b200_version", "genre_b200_voxelize_workspace_bytes",
     "genre_b200_convt_c1_wgrad_workspace_bytes", "genre_b200_conv_k8s2_wgrad_workspace_bytes",
     "genre_b200_bn_workspace_bytes", "genre_b200_render_spherical_workspace_bytes",
-    "genre_b200_voxel_surface_workspace_bytes", "genre_b200_conv_set_tma", "genre_b200_convflat_positions", "genre_b200_skinny_gemm_workspace_bytes"])
+    "genre_b200_voxel_surface_workspace_bytes", "genre_b200_conv_set_tma", "genre_b200_conv_set_cluster", "genre_b200_convflat_positions", "genre_b200_skinny_gemm_workspace_bytes"])
 
 _lib = None
 launch_count = 0  # kernels of this library enqueued through the binding (bench.py reports it as gpu_launches)
@@ -131,6 +131,8 @@ def load():
     lib.genre_b200_render_spherical_workspace_bytes.argtypes = [_i64, _int]
     lib.genre_b200_conv_set_tma.restype = _int
     lib.genre_b200_conv_set_tma.argtypes = [_int]
+    lib.genre_b200_conv_set_cluster.restype = _int
+    lib.genre_b200_conv_set_cluster.argtypes = [_int]
     lib.genre_b200_skinny_gemm_workspace_bytes.restype = _size
     lib.genre_b200_skinny_gemm_workspace_bytes.argtypes = [_i64, _i64, _i64, _int]
     lib.genre_b200_convflat_positions.restype = _i64

@@ -166,12 +166,18 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
     return zi >= 0 && zi < p.D;
   };
   const int n_q = TZ * nchunk * Cfg::YS;
+  // Cluster of NCL CTAs along blockIdx.x (same parity class, hence the same weight sequence): every CTA fetches 1/NCL of each
+  // stage's weights and multicasts it to all of them, so the L2 serves the weights once per cluster instead of once per CTA.
+  // The CTAs then walk the SAME stage sequence in lockstep: a stage whose z-tap plane lies outside this CTA's volume is not
+  // skipped but walked without halo and without MMAs; a slot is free when every CTA's MMAs have released it.
+  const uint32_t ncl = cluster_nctarank(), crank = ncl > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << ncl) - 1);
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full[s], TMA ? 1 : CT_PRODUCERS + 1);  // cp.async path: 128 producer arrivals + the expect_tx arrival of the
                                                         // weight copy; TMA path: the one expect_tx arrival (halo + weight bytes)
-      mbar_init(&empty[s], 1);                // one tcgen05.commit
+      mbar_init(&empty[s], ncl);              // one tcgen05.commit per CTA of the cluster
     }
     mbar_init(accum_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,8 +190,18 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
   }
   tc_fence_before();
   __syncthreads();
+  if (ncl > 1) cluster_sync_all();   // every CTA's barriers exist before a peer's multicast can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // weights of one stage: this CTA's slice, to every CTA of the cluster
+  auto load_weights = [&](uint8_t *dst, const float *wsrc, uint32_t bytes, uint64_t *bar) {
+    if (ncl == 1) {
+      bulk_g2s(dst, wsrc, bytes, bar);
+    } else {
+      const uint32_t slice = bytes / ncl;
+      bulk_g2s_multicast(dst + crank * slice, reinterpret_cast<const uint8_t *>(wsrc) + crank * slice, slice, bar, cmask);
+    }
+  };
 
   if (warp < 4) {
     if constexpr (TMA) {
@@ -194,7 +210,8 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
         int it = 0;
         for (int q = 0; q < n_q; ++q) {
           int tz, kc, ys, bz, by, bx;
-          if (!stage_of(q, tz, kc, ys, bz, by, bx)) continue;
+          const bool valid = stage_of(q, tz, kc, ys, bz, by, bx);
+          if (!valid && ncl == 1) continue;
           const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
           ++it;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
@@ -203,8 +220,9 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
           const uint32_t wbytes = (uint32_t)(rows * T * Cfg::B_TAP_BYTES);
           const float *wsrc = p.wpack + ((((size_t)par * TZ + tz) * nchunk + kc) * (size_t)(T * T * Cfg::B_TAP_BYTES / 4)) +
                               (size_t)ys * Cfg::ROWS * T * (Cfg::B_TAP_BYTES / 4);
-          mbar_arrive_expect_tx(&full[s], wbytes + (uint32_t)Cfg::A_TX_BYTES);
-          bulk_g2s(sa + Cfg::A_BYTES, wsrc, wbytes, &full[s]);
+          mbar_arrive_expect_tx(&full[s], wbytes + (valid ? (uint32_t)Cfg::A_TX_BYTES : 0u));
+          load_weights(sa + Cfg::A_BYTES, wsrc, wbytes, &full[s]);
+          if (!valid) continue;
           const int zi = zj + bz - tz;
           const int gy0 = y0 + by - (T - 1), gx0 = x0 + bx - (T - 1);
 #pragma unroll
@@ -243,7 +261,8 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
     };
     for (int q = 0; q < n_q; ++q) {
       int tz, kc, ys, bz, by, bx;
-      if (!stage_of(q, tz, kc, ys, bz, by, bx)) continue;
+      const bool valid = stage_of(q, tz, kc, ys, bz, by, bx);
+      if (!valid && ncl == 1) continue;
       const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
       uint8_t *sa = stages + (size_t)s * Cfg::STAGE_BYTES;
@@ -254,10 +273,11 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
         const float *wsrc = p.wpack + ((((size_t)par * TZ + tz) * nchunk + kc) * (size_t)(T * T * Cfg::B_TAP_BYTES / 4)) +
                             (size_t)ys * Cfg::ROWS * T * (Cfg::B_TAP_BYTES / 4);
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(sa + Cfg::A_BYTES, wsrc, bytes, &full[s]);
+        load_weights(sa + Cfg::A_BYTES, wsrc, bytes, &full[s]);
       }
       const int zi = zj + bz - tz;
       const int gy0 = y0 + by - (T - 1), gx0 = x0 + bx - (T - 1);  // halo row hy holds input row gy0 + hy
+      if (valid) {
 #pragma unroll
       for (int part = 0; part < Cfg::PARTS; ++part) {
 #pragma unroll
@@ -277,6 +297,7 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
             cp_async16_zfill(sa + (part * CT_KCG + c) * Cfg::A_CG_STRIDE + hoff[i], g, ok);
           }
         }
+      }
       }
       publish();
     }
@@ -401,11 +422,13 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
     int it = 0;
     for (int q = 0; q < n_q; ++q) {
       int tz, kc, ys, bz, by, bx;
-      if (!stage_of(q, tz, kc, ys, bz, by, bx)) continue;
+      const bool valid = stage_of(q, tz, kc, ys, bz, by, bx);
+      if (!valid && ncl == 1) continue;
       const int s = it % Cfg::STAGES, use = it / Cfg::STAGES;
       ++it;
       mbar_wait(&full[s], use & 1);
       tc_fence_after();
+      if (valid) {
       const uint32_t sa = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES);
       const uint32_t sb = sa + Cfg::A_BYTES;
       const int ty0 = ys * Cfg::ROWS;
@@ -432,11 +455,15 @@ convt3d_s2_kernel(const ConvTParams p, const __grid_constant__ CUtensorMap tmap0
         }
       }
       first = false;
-      umma_commit(&empty[s]);  // frees the slot when the MMAs that read it are done (implies fence::before_thread_sync)
+      }
+      // frees the slot (in every CTA of the cluster) when the MMAs that read it are done (implies fence::before_thread_sync)
+      if (ncl == 1) umma_commit(&empty[s]);
+      else umma_commit_multicast(&empty[s], cmask);
     }
     umma_commit(accum_full);
   }
   __syncthreads();
+  if (ncl > 1) cluster_sync_all();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
@@ -482,6 +509,17 @@ static bool conv_use_tma() {
   return g_conv_tma == 1 && tmap_encoder() != nullptr;
 }
 
+// CTAs per cluster sharing each stage's weights by multicast (GENRE_B200_CONV_CLUSTER, or genre_b200_conv_set_cluster): 1 = off
+static int g_conv_cluster = -1;
+static int conv_cluster() {
+  if (g_conv_cluster < 0) {
+    const char *e = getenv("GENRE_B200_CONV_CLUSTER");
+    const int v = e ? atoi(e) : 1;
+    g_conv_cluster = (v == 2 || v == 4 || v == 8) ? v : 1;
+  }
+  return g_conv_cluster;
+}
+
 template <int TZ, int T, int NPAD, int MT, int MODE, int OP, bool TMA>
 static int launch_convt_variant(const ConvTParams &p, cudaStream_t st) {
   using Cfg = ConvTCfg<T, NPAD, MT, OP == 2, TMA>;
@@ -511,6 +549,24 @@ static int launch_convt_variant(const ConvTParams &p, cudaStream_t st) {
       return fail_arg(GENRE_B200_EINVAL, "convt3d: cuTensorMapEncodeTiled failed for the second operand");
   }
   dim3 grid((unsigned)(p.B * p.D * (p.H / CT_BY) * q.xtiles), MODE == 0 ? 8 : MODE == 2 ? 2 : 1);
+  int cl = conv_cluster();
+  while (cl > 1 && (grid.x % cl != 0 || (T * Cfg::B_TAP_BYTES) % (16 * cl) != 0)) cl /= 2;
+  if (cl > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(CT_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, q, tm0, tm1) != cudaSuccess) return check_launch("convt3d_s2 cluster launch");
+    return check_launch("convt3d_s2 kernel");
+  }
   kern<<<grid, CT_THREADS, Cfg::SMEM, st>>>(q, tm0, tm1);
   return check_launch("convt3d_s2 kernel");
 }
@@ -566,6 +622,14 @@ using namespace gb;
 extern "C" int genre_b200_conv_set_tma(int enable) {
   const int prev = conv_use_tma() ? 1 : 0;
   g_conv_tma = enable ? 1 : 0;
+  return prev;
+}
+
+// CTAs per thread-block cluster of the convolution kernels (1, 2, 4 or 8): the CTAs of a cluster share every stage's weights
+// through multicast bulk copies.  Returns the previous setting.  Process-wide; for A/B timing and tests.
+extern "C" int genre_b200_conv_set_cluster(int ctas) {
+  const int prev = conv_cluster();
+  g_conv_cluster = (ctas == 2 || ctas == 4 || ctas == 8) ? ctas : 1;
   return prev;
 }
 
