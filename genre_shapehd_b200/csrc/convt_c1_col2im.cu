@@ -14,9 +14,11 @@
 //
 // CTA = one (sample, band of 8 input rows), sweeping z.  Per z step: 512 positions (4 M-tiles of 2 rows x 64) x 64 taps are
 // accumulated in TMEM (fp16 operands; OP 2 = the fp32-accurate hi/lo split of convt3d.cu: columns [0,64) hi*hi, [64,128) the
-// 2^11-scaled cross terms), then 8 epilogue warps scatter-add them into a ring of four output planes in shared memory.  Taps are
-// processed in 8 phases t = (kz>>1, ky>>1, kx>>1): within a phase the 8 taps of a position hit the 8 parity classes and different
-// positions hit different cells, so the adds are race-free without atomics; a barrier separates phases.  Output planes
+// 2^11-scaled cross terms), then 8 epilogue warps add them into a ring of four output planes in shared memory.  Along x the two
+// contributions of an output are summed in registers (warp shuffles; the two lanes at a warp seam exchange through a scratch), and
+// the taps are processed in 4 phases (kz>>1, ky>>1): within a phase a position adds one float2 (outputs 2x, 2x+1) to each of 4
+// (kz, ky) rows, different positions hit different cells, so the adds are race-free without atomics; a barrier separates phases
+// (shared-memory traffic: 1/4 of a per-tap scatter, and conflict-free).  Output planes
 // 2z-1 and 2z are complete after step z (their other contributions came from step z-1, carried in the ring) and leave with
 // 16-byte stores.  Only the two output rows on each side of a band are shared with the neighbouring band's CTA: those are
 // added with red.global.add.v4.f32 onto zeroed rows (two commutative contributions: deterministic), zeroed by one strided
@@ -50,31 +52,15 @@ struct ColParams {
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// issue 2 (or 4 with the lo halves) 8-column TMEM loads, then one wait
-template <bool X2>
-__device__ __forceinline__ void tmem_ld_phase(uint32_t t0, uint32_t t1, float (&h0)[8], float (&h1)[8], float (&l0)[8], float (&l1)[8]) {
-  uint32_t a[8], b[8], c[8], d[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "r"(t0) : "memory");
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]) : "r"(t1) : "memory");
-  if (X2) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]) : "r"(t0 + 64) : "memory");
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]) : "r"(t1 + 64) : "memory");
-  }
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h0[i] = __uint_as_float(a[i]);
-    h1[i] = __uint_as_float(b[i]);
-    if (X2) {
-      l0[i] = __uint_as_float(c[i]);
-      l1[i] = __uint_as_float(d[i]);
-    }
-  }
+// 16 accumulator columns of this thread's row, no wait (tmem_ld_wait() before the registers are read)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -192,8 +178,12 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
     const int Ho = 2 * p.H, Do = 2 * p.D;
     constexpr int Wo = 2 * CI_W;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    float *base0 = ring + (2 * yl0) * CI_PITCH + 2 * x + 3;
-    float *base1 = ring + (2 * yl1) * CI_PITCH + 2 * x + 3;
+    // ring cell of output column ox = 2x of this thread's two input rows (column ox + 4: even, so an (ox, ox + 1) pair is one float2)
+    float *base0 = ring + (2 * yl0) * CI_PITCH + 2 * x + 4;
+    float *base1 = ring + (2 * yl1) * CI_PITCH + 2 * x + 4;
+    const int xhalf = quarter & 1, ysub = quarter >> 1;
+    // taps kx = 3 of x = 31 and kx = 0 of x = 32 belong to cells of the neighbouring warp: exchanged through this scratch
+    float *scr = reinterpret_cast<float *>(tmem_slot + 2);   // [2 buffers][4 M-tiles][2 rows][2 directions][4 (rz,ry)]
 
     auto flush_plane = [&](int slot, int oz) {   // complete plane -> global, ring slot back to zero
       float *pl = ring + slot * CI_PLANE;
@@ -216,26 +206,72 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
       mbar_wait(tmem_full, z & 1);
       tc_fence_after();
       const int zs = (2 * z) & 3;   // ring slot of tap kz = 0 (output plane 2z - 1); tap kz uses (zs + kz) & 3
+      // 4 phases (tz, ty): the 16 taps (rz, ry, kx = 0..3) of a position.  Along x the two contributions of an output are
+      // summed in registers first (ox = 2x: kx = 1 of x and kx = 3 of x - 1; ox = 2x + 1: kx = 2 of x and kx = 0 of x + 1, via
+      // warp shuffles), so a position adds ONE float2 per (kz, ky) to the ring: distinct cells for distinct positions.
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        float h0[8], h1[8], l0[8], l1[8];
-        tmem_ld_phase<X2>(trow + (uint32_t)((2 * half) * NACC + t * 8), trow + (uint32_t)((2 * half + 1) * NACC + t * 8), h0, h1, l0, l1);
-        if (t == 7) {   // last TMEM read of this step: the MMA warp may overwrite the accumulators
+      for (int ph = 0; ph < 4; ++ph) {
+        const int tz = ph >> 1, ty = ph & 1;
+        uint32_t rh0[16], rh1[16], rl0[16], rl1[16];
+        const uint32_t c0 = (uint32_t)((2 * half) * NACC + ph * 16), c1 = (uint32_t)((2 * half + 1) * NACC + ph * 16);
+        tmem_ld16_nowait(trow + c0, rh0);
+        tmem_ld16_nowait(trow + c1, rh1);
+        if constexpr (X2) {
+          tmem_ld16_nowait(trow + c0 + 64, rl0);
+          tmem_ld16_nowait(trow + c1 + 64, rl1);
+        }
+        tmem_ld_wait();
+        if (ph == 3) {   // last TMEM read of this step: the MMA warp may overwrite the accumulators
           tc_fence_before();
           mbar_arrive(tmem_empty);
         }
-        const int tz = (t >> 2) & 1, ty = (t >> 1) & 1, tx = t & 1;
+        float v0[16], v1[16];   // index tx * 8 + rz * 4 + ry * 2 + rx, kx = 2 tx + rx
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int kz = 2 * tz + ((r >> 2) & 1), ky = 2 * ty + ((r >> 1) & 1), kx = 2 * tx + (r & 1);
-          const int off = ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH + kx;
-          const float v0 = X2 ? fmaf(l0[r], LO_SCALE, h0[r]) : h0[r];
-          const float v1 = X2 ? fmaf(l1[r], LO_SCALE, h1[r]) : h1[r];
-          base0[off] += v0;
-          base1[off] += v1;
+        for (int i = 0; i < 16; ++i) {
+          v0[i] = X2 ? fmaf(__uint_as_float(rl0[i]), LO_SCALE, __uint_as_float(rh0[i])) : __uint_as_float(rh0[i]);
+          v1[i] = X2 ? fmaf(__uint_as_float(rl1[i]), LO_SCALE, __uint_as_float(rh1[i])) : __uint_as_float(rh1[i]);
         }
-        named_bar_sync(1, CI_EPI_WARPS * 32);
+        float *sb = scr + (ph & 1) * 64;
+        if (lane == 31 && xhalf == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sb[(((2 * half) * 2 + ysub) * 2 + 0) * 4 + j] = v0[8 + 2 * j + 1];       // kx = 3
+            sb[(((2 * half + 1) * 2 + ysub) * 2 + 0) * 4 + j] = v1[8 + 2 * j + 1];
+          }
+        }
+        if (lane == 0 && xhalf == 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sb[(((2 * half) * 2 + ysub) * 2 + 1) * 4 + j] = v0[2 * j];               // kx = 0
+            sb[(((2 * half + 1) * 2 + ysub) * 2 + 1) * 4 + j] = v1[2 * j];
+          }
+        }
+        named_bar_sync(1, CI_EPI_WARPS * 32);   // scratch visible; the previous phase's adds are done
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {           // j = rz * 2 + ry
+          const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
+          const int off = ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH;
+          float up0 = __shfl_up_sync(0xffffffffu, v0[8 + 2 * j + 1], 1), dn0 = __shfl_down_sync(0xffffffffu, v0[2 * j], 1);
+          float up1 = __shfl_up_sync(0xffffffffu, v1[8 + 2 * j + 1], 1), dn1 = __shfl_down_sync(0xffffffffu, v1[2 * j], 1);
+          if (lane == 0) {
+            up0 = xhalf ? sb[(((2 * half) * 2 + ysub) * 2 + 0) * 4 + j] : 0.0f;      // x = 0: output -1 does not exist
+            up1 = xhalf ? sb[(((2 * half + 1) * 2 + ysub) * 2 + 0) * 4 + j] : 0.0f;
+          }
+          if (lane == 31) {
+            dn0 = xhalf ? 0.0f : sb[(((2 * half) * 2 + ysub) * 2 + 1) * 4 + j];      // x = 63: output 128 does not exist
+            dn1 = xhalf ? 0.0f : sb[(((2 * half + 1) * 2 + ysub) * 2 + 1) * 4 + j];
+          }
+          float2 *cell0 = reinterpret_cast<float2 *>(base0 + off), *cell1 = reinterpret_cast<float2 *>(base1 + off);
+          float2 a0 = *cell0, a1 = *cell1;
+          a0.x += v0[2 * j + 1] + up0;      // ox = 2x:     kx = 1 here + kx = 3 of x - 1
+          a0.y += v0[8 + 2 * j] + dn0;      // ox = 2x + 1: kx = 2 here + kx = 0 of x + 1
+          a1.x += v1[2 * j + 1] + up1;
+          a1.y += v1[8 + 2 * j] + dn1;
+          *cell0 = a0;
+          *cell1 = a1;
+        }
       }
+      named_bar_sync(1, CI_EPI_WARPS * 32);     // all adds of this step are in the ring
       // planes 2z - 1 (tap kz = 0) and 2z (kz = 1) have received everything
       if (z > 0) flush_plane(zs, 2 * z - 1);
       else {      // output plane -1 does not exist: drop what tap kz = 0 of the first step scattered
@@ -260,7 +296,7 @@ template <int OP>
 static int launch_col2im(ColParams &p, cudaStream_t st) {
   constexpr int PARTS = OP == 2 ? 2 : 1, NACC = PARTS * 64;
   constexpr int STAGE_BYTES = PARTS * 2 * CI_POS * 16;
-  const int fixed = p.ksteps * 2 * (NACC / 8) * 128 + 4 * CI_PLANE * 4 + 256;
+  const int fixed = p.ksteps * 2 * (NACC / 8) * 128 + 4 * CI_PLANE * 4 + 1024;   // weights + plane ring + barriers, TMEM slot, exchange scratch
   int stages = (226 * 1024 - fixed) / STAGE_BYTES;
   if (stages > CI_MAX_STAGES) stages = CI_MAX_STAGES;
   GB_REQUIRE(stages >= 2, GENRE_B200_EINVAL, "convt_c1_col2im: %d K steps of weights leave no room for the pipeline", p.ksteps);
