@@ -209,27 +209,33 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
       // 4 phases (tz, ty): the 16 taps (rz, ry, kx = 0..3) of a position.  Along x the two contributions of an output are
       // summed in registers first (ox = 2x: kx = 1 of x and kx = 3 of x - 1; ox = 2x + 1: kx = 2 of x and kx = 0 of x + 1, via
       // warp shuffles), so a position adds ONE float2 per (kz, ky) to the ring: distinct cells for distinct positions.
+      // The TMEM reads of phase ph + 1 (hi halves) are issued before the adds of phase ph: their latency hides behind the
+      // shared-memory work; a row loads its 4 ring cells before it touches any of them (no load-add-store chains).
+      uint32_t rh0[16], rh1[16], rl0[16], rl1[16];
+      auto issue_hi = [&](int ph) {
+        tmem_ld16_nowait(trow + (uint32_t)((2 * half) * NACC + ph * 16), rh0);
+        tmem_ld16_nowait(trow + (uint32_t)((2 * half + 1) * NACC + ph * 16), rh1);
+      };
+      issue_hi(0);
 #pragma unroll
       for (int ph = 0; ph < 4; ++ph) {
         const int tz = ph >> 1, ty = ph & 1;
-        uint32_t rh0[16], rh1[16], rl0[16], rl1[16];
-        const uint32_t c0 = (uint32_t)((2 * half) * NACC + ph * 16), c1 = (uint32_t)((2 * half + 1) * NACC + ph * 16);
-        tmem_ld16_nowait(trow + c0, rh0);
-        tmem_ld16_nowait(trow + c1, rh1);
-        if constexpr (X2) {
-          tmem_ld16_nowait(trow + c0 + 64, rl0);
-          tmem_ld16_nowait(trow + c1 + 64, rl1);
+        if constexpr (X2) {   // the cross-term halves are fetched now (prefetching them as well does not fit the register file)
+          tmem_ld16_nowait(trow + (uint32_t)((2 * half) * NACC + 64 + ph * 16), rl0);
+          tmem_ld16_nowait(trow + (uint32_t)((2 * half + 1) * NACC + 64 + ph * 16), rl1);
         }
         tmem_ld_wait();
-        if (ph == 3) {   // last TMEM read of this step: the MMA warp may overwrite the accumulators
-          tc_fence_before();
-          mbar_arrive(tmem_empty);
-        }
         float v0[16], v1[16];   // index tx * 8 + rz * 4 + ry * 2 + rx, kx = 2 tx + rx
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           v0[i] = X2 ? fmaf(__uint_as_float(rl0[i]), LO_SCALE, __uint_as_float(rh0[i])) : __uint_as_float(rh0[i]);
           v1[i] = X2 ? fmaf(__uint_as_float(rl1[i]), LO_SCALE, __uint_as_float(rh1[i])) : __uint_as_float(rh1[i]);
+        }
+        if (ph < 3) {
+          issue_hi(ph + 1);
+        } else {        // the last TMEM read of this step has landed: the MMA warp may overwrite the accumulators
+          tc_fence_before();
+          mbar_arrive(tmem_empty);
         }
         float *sb = scr + (ph & 1) * 64;
         if (lane == 31 && xhalf == 0) {
@@ -247,29 +253,29 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
           }
         }
         named_bar_sync(1, CI_EPI_WARPS * 32);   // scratch visible; the previous phase's adds are done
+        auto add_row = [&](const float (&v)[16], float *base, int mt) {
+          float2 a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {           // j = rz * 2 + ry
-          const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
-          const int off = ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH;
-          float up0 = __shfl_up_sync(0xffffffffu, v0[8 + 2 * j + 1], 1), dn0 = __shfl_down_sync(0xffffffffu, v0[2 * j], 1);
-          float up1 = __shfl_up_sync(0xffffffffu, v1[8 + 2 * j + 1], 1), dn1 = __shfl_down_sync(0xffffffffu, v1[2 * j], 1);
-          if (lane == 0) {
-            up0 = xhalf ? sb[(((2 * half) * 2 + ysub) * 2 + 0) * 4 + j] : 0.0f;      // x = 0: output -1 does not exist
-            up1 = xhalf ? sb[(((2 * half + 1) * 2 + ysub) * 2 + 0) * 4 + j] : 0.0f;
+          for (int j = 0; j < 4; ++j) {           // j = rz * 2 + ry
+            const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
+            a[j] = *reinterpret_cast<const float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH);
           }
-          if (lane == 31) {
-            dn0 = xhalf ? 0.0f : sb[(((2 * half) * 2 + ysub) * 2 + 1) * 4 + j];      // x = 63: output 128 does not exist
-            dn1 = xhalf ? 0.0f : sb[(((2 * half + 1) * 2 + ysub) * 2 + 1) * 4 + j];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float up = __shfl_up_sync(0xffffffffu, v[8 + 2 * j + 1], 1), dn = __shfl_down_sync(0xffffffffu, v[2 * j], 1);
+            if (lane == 0) up = xhalf ? sb[((mt * 2 + ysub) * 2 + 0) * 4 + j] : 0.0f;     // x = 0: output -1 does not exist
+            if (lane == 31) dn = xhalf ? 0.0f : sb[((mt * 2 + ysub) * 2 + 1) * 4 + j];    // x = 63: output 128 does not exist
+            a[j].x += v[2 * j + 1] + up;      // ox = 2x:     kx = 1 here + kx = 3 of x - 1
+            a[j].y += v[8 + 2 * j] + dn;      // ox = 2x + 1: kx = 2 here + kx = 0 of x + 1
           }
-          float2 *cell0 = reinterpret_cast<float2 *>(base0 + off), *cell1 = reinterpret_cast<float2 *>(base1 + off);
-          float2 a0 = *cell0, a1 = *cell1;
-          a0.x += v0[2 * j + 1] + up0;      // ox = 2x:     kx = 1 here + kx = 3 of x - 1
-          a0.y += v0[8 + 2 * j] + dn0;      // ox = 2x + 1: kx = 2 here + kx = 0 of x + 1
-          a1.x += v1[2 * j + 1] + up1;
-          a1.y += v1[8 + 2 * j] + dn1;
-          *cell0 = a0;
-          *cell1 = a1;
-        }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
+            *reinterpret_cast<float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH) = a[j];
+          }
+        };
+        add_row(v0, base0, 2 * half);
+        add_row(v1, base1, 2 * half + 1);
       }
       named_bar_sync(1, CI_EPI_WARPS * 32);     // all adds of this step are in the ring
       // planes 2z - 1 (tap kz = 0) and 2z (kz = 1) have received everything
