@@ -14,7 +14,7 @@
 //
 // CTA = one (sample, band of 8 input rows), sweeping z.  Per z step: 512 positions (4 M-tiles of 2 rows x 64) x 64 taps are
 // accumulated in TMEM (fp16 operands; OP 2 = the fp32-accurate hi/lo split of convt3d.cu: columns [0,64) hi*hi, [64,128) the
-// 2^11-scaled cross terms), then 8 epilogue warps add them into a ring of four output planes in shared memory.  Along x the two
+// 2^11-scaled cross terms), then 16 epilogue warps (one thread per position) add them into a ring of four output planes in shared memory.  Along x the two
 // contributions of an output are summed in registers (warp shuffles; the two lanes at a warp seam exchange through a scratch), and
 // the taps are processed in 4 phases (kz>>1, ky>>1): within a phase a position adds one float2 (outputs 2x, 2x+1) to each of 4
 // (kz, ky) rows, different positions hit different cells, so the adds are race-free without atomics; a barrier separates phases
@@ -33,7 +33,7 @@ constexpr int CI_W = 64;             // input width (positions per row)
 constexpr int CI_ROWS = 8;           // input rows per band
 constexpr int CI_POS = CI_W * CI_ROWS;   // positions per z step = 4 M-tiles
 constexpr int CI_MT = 4;
-constexpr int CI_EPI_WARPS = 8;
+constexpr int CI_EPI_WARPS = 16;          // one warp per (M-tile, TMEM lane quarter): a thread owns one input position per z step
 constexpr int CI_THREADS = (CI_EPI_WARPS + 2) * 32;   // + MMA warp + producer warp
 constexpr int CI_MAX_STAGES = 6;
 constexpr int CI_UY = 2 * CI_ROWS + 2;   // output rows touched by a band
@@ -167,11 +167,11 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
     }
   } else {
     // ===================== epilogue: TMEM -> scatter-add into the plane ring -> global ================================
-    const int etid = tid;                                 // 0..255
-    const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter of this warp; M-tiles {2 half, 2 half + 1}
-    const int row = quarter * 32 + lane;                  // accumulator row within an M-tile: input row (row >> 6), x = row & 63
+    const int etid = tid;                                 // 0..511
+    const int quarter = warp & 3, mt = warp >> 2;         // TMEM lane quarter of this warp; its M-tile
+    const int row = quarter * 32 + lane;                  // accumulator row within the M-tile: input row (row >> 6), x = row & 63
     const int x = row & 63;
-    const int yl0 = (2 * half) * 2 + (row >> 6), yl1 = (2 * half + 1) * 2 + (row >> 6);   // input rows of this thread's two M-tiles
+    const int yl = 2 * mt + (row >> 6);                   // input row of this thread within the band
     for (int i = etid; i < 4 * CI_PLANE; i += CI_EPI_WARPS * 32) ring[i] = 0.0f;
     named_bar_sync(1, CI_EPI_WARPS * 32);
     const float bias = __ldg(p.bias);
@@ -179,8 +179,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
     constexpr int Wo = 2 * CI_W;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     // ring cell of output column ox = 2x of this thread's two input rows (column ox + 4: even, so an (ox, ox + 1) pair is one float2)
-    float *base0 = ring + (2 * yl0) * CI_PITCH + 2 * x + 4;
-    float *base1 = ring + (2 * yl1) * CI_PITCH + 2 * x + 4;
+    float *base = ring + (2 * yl) * CI_PITCH + 2 * x + 4;
     const int xhalf = quarter & 1, ysub = quarter >> 1;
     // taps kx = 3 of x = 31 and kx = 0 of x = 32 belong to cells of the neighbouring warp: exchanged through this scratch
     float *scr = reinterpret_cast<float *>(tmem_slot + 2);   // [2 buffers][4 M-tiles][2 rows][2 directions][4 (rz,ry)]
@@ -209,73 +208,53 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
       // 4 phases (tz, ty): the 16 taps (rz, ry, kx = 0..3) of a position.  Along x the two contributions of an output are
       // summed in registers first (ox = 2x: kx = 1 of x and kx = 3 of x - 1; ox = 2x + 1: kx = 2 of x and kx = 0 of x + 1, via
       // warp shuffles), so a position adds ONE float2 per (kz, ky) to the ring: distinct cells for distinct positions.
-      // The TMEM reads of phase ph + 1 (hi halves) are issued before the adds of phase ph: their latency hides behind the
-      // shared-memory work; a row loads its 4 ring cells before it touches any of them (no load-add-store chains).
-      uint32_t rh0[16], rh1[16], rl0[16], rl1[16];
-      auto issue_hi = [&](int ph) {
-        tmem_ld16_nowait(trow + (uint32_t)((2 * half) * NACC + ph * 16), rh0);
-        tmem_ld16_nowait(trow + (uint32_t)((2 * half + 1) * NACC + ph * 16), rh1);
-      };
-      issue_hi(0);
+      // The TMEM read of phase ph + 1 (hi half) is issued before the adds of phase ph: its latency hides behind the
+      // shared-memory work; the 4 ring cells are loaded before any of them is touched (no load-add-store chains).
+      uint32_t rh[16], rl[16];
+      tmem_ld16_nowait(trow + (uint32_t)(mt * NACC), rh);
 #pragma unroll
       for (int ph = 0; ph < 4; ++ph) {
         const int tz = ph >> 1, ty = ph & 1;
-        if constexpr (X2) {   // the cross-term halves are fetched now (prefetching them as well does not fit the register file)
-          tmem_ld16_nowait(trow + (uint32_t)((2 * half) * NACC + 64 + ph * 16), rl0);
-          tmem_ld16_nowait(trow + (uint32_t)((2 * half + 1) * NACC + 64 + ph * 16), rl1);
-        }
+        if constexpr (X2) tmem_ld16_nowait(trow + (uint32_t)(mt * NACC + 64 + ph * 16), rl);
         tmem_ld_wait();
-        float v0[16], v1[16];   // index tx * 8 + rz * 4 + ry * 2 + rx, kx = 2 tx + rx
+        float v[16];   // index tx * 8 + rz * 4 + ry * 2 + rx, kx = 2 tx + rx
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v0[i] = X2 ? fmaf(__uint_as_float(rl0[i]), LO_SCALE, __uint_as_float(rh0[i])) : __uint_as_float(rh0[i]);
-          v1[i] = X2 ? fmaf(__uint_as_float(rl1[i]), LO_SCALE, __uint_as_float(rh1[i])) : __uint_as_float(rh1[i]);
-        }
+        for (int i = 0; i < 16; ++i) v[i] = X2 ? fmaf(__uint_as_float(rl[i]), LO_SCALE, __uint_as_float(rh[i])) : __uint_as_float(rh[i]);
         if (ph < 3) {
-          issue_hi(ph + 1);
+          tmem_ld16_nowait(trow + (uint32_t)(mt * NACC + (ph + 1) * 16), rh);
         } else {        // the last TMEM read of this step has landed: the MMA warp may overwrite the accumulators
           tc_fence_before();
           mbar_arrive(tmem_empty);
         }
-        float *sb = scr + (ph & 1) * 64;
+        float *sb = scr + (ph & 1) * 64 + (mt * 2 + ysub) * 8;
         if (lane == 31 && xhalf == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sb[(((2 * half) * 2 + ysub) * 2 + 0) * 4 + j] = v0[8 + 2 * j + 1];       // kx = 3
-            sb[(((2 * half + 1) * 2 + ysub) * 2 + 0) * 4 + j] = v1[8 + 2 * j + 1];
-          }
+          for (int j = 0; j < 4; ++j) sb[j] = v[8 + 2 * j + 1];       // kx = 3 of x = 31
         }
         if (lane == 0 && xhalf == 1) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sb[(((2 * half) * 2 + ysub) * 2 + 1) * 4 + j] = v0[2 * j];               // kx = 0
-            sb[(((2 * half + 1) * 2 + ysub) * 2 + 1) * 4 + j] = v1[2 * j];
-          }
+          for (int j = 0; j < 4; ++j) sb[4 + j] = v[2 * j];           // kx = 0 of x = 32
         }
         named_bar_sync(1, CI_EPI_WARPS * 32);   // scratch visible; the previous phase's adds are done
-        auto add_row = [&](const float (&v)[16], float *base, int mt) {
-          float2 a[4];
+        float2 a[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {           // j = rz * 2 + ry
-            const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
-            a[j] = *reinterpret_cast<const float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH);
-          }
+        for (int j = 0; j < 4; ++j) {           // j = rz * 2 + ry
+          const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
+          a[j] = *reinterpret_cast<const float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH);
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float up = __shfl_up_sync(0xffffffffu, v[8 + 2 * j + 1], 1), dn = __shfl_down_sync(0xffffffffu, v[2 * j], 1);
-            if (lane == 0) up = xhalf ? sb[((mt * 2 + ysub) * 2 + 0) * 4 + j] : 0.0f;     // x = 0: output -1 does not exist
-            if (lane == 31) dn = xhalf ? 0.0f : sb[((mt * 2 + ysub) * 2 + 1) * 4 + j];    // x = 63: output 128 does not exist
-            a[j].x += v[2 * j + 1] + up;      // ox = 2x:     kx = 1 here + kx = 3 of x - 1
-            a[j].y += v[8 + 2 * j] + dn;      // ox = 2x + 1: kx = 2 here + kx = 0 of x + 1
-          }
+        for (int j = 0; j < 4; ++j) {
+          float up = __shfl_up_sync(0xffffffffu, v[8 + 2 * j + 1], 1), dn = __shfl_down_sync(0xffffffffu, v[2 * j], 1);
+          if (lane == 0) up = xhalf ? sb[j] : 0.0f;          // x = 0: output -1 does not exist
+          if (lane == 31) dn = xhalf ? 0.0f : sb[4 + j];     // x = 63: output 128 does not exist
+          a[j].x += v[2 * j + 1] + up;      // ox = 2x:     kx = 1 here + kx = 3 of x - 1
+          a[j].y += v[8 + 2 * j] + dn;      // ox = 2x + 1: kx = 2 here + kx = 0 of x + 1
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
-            *reinterpret_cast<float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH) = a[j];
-          }
-        };
-        add_row(v0, base0, 2 * half);
-        add_row(v1, base1, 2 * half + 1);
+        for (int j = 0; j < 4; ++j) {
+          const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
+          *reinterpret_cast<float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH) = a[j];
+        }
       }
       named_bar_sync(1, CI_EPI_WARPS * 32);     // all adds of this step are in the ring
       // planes 2z - 1 (tap kz = 0) and 2z (kz = 1) have received everything
