@@ -210,6 +210,9 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
       // warp shuffles), so a position adds ONE float2 per (kz, ky) to the ring: distinct cells for distinct positions.
       // The TMEM read of phase ph + 1 (hi half) is issued before the adds of phase ph: its latency hides behind the
       // shared-memory work; the 4 ring cells are loaded before any of them is touched (no load-add-store chains).
+      float *pb[4];   // this position's cell row in the ring plane of tap kz
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pb[k] = base + ((zs + k) & 3) * CI_PLANE;
       uint32_t rh[16], rl[16];
       tmem_ld16_nowait(trow + (uint32_t)(mt * NACC), rh);
 #pragma unroll
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
 #pragma unroll
         for (int j = 0; j < 4; ++j) {           // j = rz * 2 + ry
           const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
-          a[j] = *reinterpret_cast<const float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH);
+          a[j] = *reinterpret_cast<const float2 *>(pb[kz] + ky * CI_PITCH);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) convt_c1_col2im_kernel(const Co
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int kz = 2 * tz + (j >> 1), ky = 2 * ty + (j & 1);
-          *reinterpret_cast<float2 *>(base + ((zs + kz) & 3) * CI_PLANE + ky * CI_PITCH) = a[j];
+          *reinterpret_cast<float2 *>(pb[kz] + ky * CI_PITCH) = a[j];
         }
       }
       named_bar_sync(1, CI_EPI_WARPS * 32);     // all adds of this step are in the ring

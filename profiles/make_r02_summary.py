@@ -107,7 +107,7 @@ def tensor_pipe(csv_name):
         per.setdefault(key, {})[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
     rows = []
     for (_, name), m in per.items():
-        if "convt3d" not in name:
+        if not any(k in name for k in ("convt3d", "convflat", "col2im")):
             continue
         t = m.get("gpu__time_duration.sum", 0.0)
         rows.append({"kernel": name, "us": t / 1e3 if t > 1e4 else t, "tensor_pipe_active_pct": m.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")})
@@ -187,7 +187,7 @@ def main():
             ("prof_op_%s.ncu-rep" % k, "r02_ncu_op_%s.csv" % k) for k in ("nnd_forward", "calc_prob_forward", "calc_prob_backward", "sph_project",
                                                                           "vox_splat", "cam_project", "sph_bp_backward", "cam_bp_backward")]:
         rows = write_ncu_csv(rep, dst)
-        for rr in rows[:12]:
+        for rr in rows[:16]:
             g = lambda m: " ".join(rr[m]).strip() if m in rr else "?"
             md.append("- `%s`: %s; dram r/w %s / %s; issue-active %s; warps-active %s; L1 hit %s; tensor pipe %s; regs %s"
                       % (rr.get("Kernel Name", ("?",))[0][:70], g("gpu__time_duration.sum"), g("dram__bytes_read.sum"), g("dram__bytes_write.sum"),

@@ -17,7 +17,7 @@ for mode in exact f16; do
      --csv --log-file $O/unet_tensor_pipe_$mode.csv python profiles/unet_breakdown.py > /dev/null 2>> $O/ncu.err
 done
 # full captures: the conv kernel of dec5, the voxeliser, the renderer
-NCU=1 ncu --profile-from-start off --set full --clock-control none -k regex:convt3d_s2_kernel -c 12 -o $O/prof_unet_convs python profiles/unet_breakdown.py > /dev/null 2>> $O/ncu.err
+NCU=1 ncu --profile-from-start off --set full --clock-control none -k "regex:convt3d_s2_kernel|convflat_kernel|col2im_kernel|skinny_n" -c 14 -o $O/prof_unet_convs python profiles/unet_breakdown.py > /dev/null 2>> $O/ncu.err
 NCU=1 ncu --profile-from-start off --set full --clock-control none -o $O/prof_render python profiles/microbench_render.py > /dev/null 2>> $O/ncu.err
 for k in nnd_forward calc_prob_forward calc_prob_backward sph_project vox_splat cam_project sph_bp_backward cam_bp_backward; do
   ncu --set full --clock-control none -k regex:$k --launch-skip 3 -c 1 -o $O/prof_op_$k python profiles/microbench_ops.py > /dev/null 2>> $O/ncu.err
