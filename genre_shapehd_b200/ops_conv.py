@@ -1,16 +1,21 @@
 """Dispatch of the 3D convolutions of networks/networks.py to the hand-written sm_100a kernels.
 
 ``conv3d(x, module)`` / ``conv_transpose3d(x, module)`` / ``deconv_skip(...)`` return the result computed by this
-library's tcgen05 kernels, or ``None`` when no kernel covers the layer (shape / dtype / device / autograd) — the
-caller then runs the layer the way the reference does (torch.nn -> cuDNN).
+library's kernels, or ``None`` when no kernel covers the layer (shape / dtype / device / autograd) — the caller then
+runs the layer the way the reference does (torch.nn -> cuDNN; in the fp32-accurate mode through ``exact_fallback``).
 
-Covered in this round (csrc/convt3d.cu): ConvTranspose3d(k in {4, 8}, stride 2, padding k/2-1) FORWARD, without
-autograd, input width 16 or 32, height a multiple of 16, Cin a multiple of 8, Cout <= 64: Unet_3D.dec4 / dec5,
-VoxelDecoder / VoxelGenerator stages at 16^3 and 32^3.  TF32 operands, FP32 accumulation (the cuDNN path the
-reference runs on current PyTorch uses TF32 by default as well).
+Kernels and what they cover (routing conditions are the ``*_supported`` predicates below, all of them tested both ways):
+  csrc/convt3d.cu          tcgen05 implicit GEMM on halo tiles: ConvTranspose3d k 4 / 8, s 2 (planes 16 or 32 wide), Conv3d
+                           k 4 s 2 via parity sub-volumes, Conv3d k 8 s 2 via space-to-depth, the 1-channel ConvTranspose3d
+                           with 27 union taps; forward under autograd too, tensor-core input gradients for the k 8 layers
+  csrc/convflat.cu         the same GEMM over a flattened, zero-separated volume for coarse sides <= 8^3 (inference)
+  csrc/convt_c1_col2im.cu  the 1-channel ConvTranspose3d on 64-wide volumes as a tap GEMM + shared-memory col2im (inference)
+  csrc/skinny_gemm.cu      Conv3d whose kernel covers its input / ConvTranspose3d of a 1^3 input: FP32 weight streaming (inference)
+  csrc/convt_c1.cu, convt_c1_wgrad.cu, bn_train.cu   FP32-pipe 1-channel stencil and its gradients; training BatchNorm3d + activation
+Operand modes: see PRECISION below ("exact" = fp16 hi/lo split, fp32-accurate, the default).
 
-Activations cross the kernel in a channel-blocked layout [B*D][C/4][H][W][4]; ``to_blocked`` / ``from_blocked``
-convert at the boundary.
+Activations cross the halo kernels in a channel-blocked layout [B*D][C/4][H][W][4] (fp32) or [B*D][parts*C/8][H][W][8] (fp16,
+hi | lo' parts); ``to_blocked`` / ``from_blocked`` / ``space_to_depth_*`` convert at the boundary (csrc/layout.cu).
 """
 import os
 
