@@ -371,3 +371,31 @@ def test_f16x2_weight_packing_is_hi_and_scaled_lo_side_by_side():
     assert ((rec - plain).abs() <= 2.0 ** -21 * plain.abs() + 2e-11).all()
     with ops_conv.precision("f16x2"), ops_conv._forced_mode("tf32"):      # gradient convolutions keep fp32's exponent range
         assert ops_conv._mode() == "fp32x3"
+
+
+def test_f16x2_operand_split_error_bound():
+    """The arithmetic of the default conv mode, restated in numpy: hi = fp16(a), lo' = fp16((a - hi) * 2^11), the products hi*hi and
+    hi*lo' + lo'*hi in separate fp32 accumulators, result acc_hi + 2^-11 * acc_cross.  What the split drops is the lo*lo term
+    (2^-22 relative) and the rounding of lo' (2^-11 of 2^-11): a K = 5120 dot product (Unet_3D.dec2's) stays within 2e-6 of the
+    exact value relative to sum |a||w|, three orders of magnitude inside the 1e-4 the whole nets are tested at."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    k = 5120
+    a = (rng.standard_normal((64, k)) * np.exp(rng.uniform(-3, 3, (64, 1)))).astype(np.float32)
+    w = (rng.standard_normal((k, 32)) * 0.05).astype(np.float32)
+
+    def split(t):
+        hi = t.astype(np.float16)
+        lo = ((t - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+        return hi.astype(np.float32), lo.astype(np.float32)
+    ah, al = split(a)
+    wh, wl = split(w)
+    assert np.all(np.isfinite(al)) and np.all(np.isfinite(wl))
+    acc_hi = ah @ wh                                   # fp32 accumulation
+    acc_cross = ah @ wl + al @ wh
+    got = acc_hi + acc_cross * np.float32(1.0 / 2048.0)
+    ref = a.astype(np.float64) @ w.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64)
+    assert np.max(np.abs(got - ref) / scale) < 2e-6
+    single = ah @ wh                                   # the opt-in single-pass fp16 mode keeps only this term
+    assert np.max(np.abs(single - ref) / scale) > 1e-5
