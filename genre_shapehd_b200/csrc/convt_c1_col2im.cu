@@ -14,13 +14,13 @@
 //
 // CTA = one (sample, band of 8 input rows), sweeping z.  Per z step: 512 positions (4 M-tiles of 2 rows x 64) x 64 taps are
 // accumulated in TMEM (fp16 operands; OP 2 = the fp32-accurate hi/lo split of convt3d.cu: columns [0,64) hi*hi, [64,128) the
-// 2^11-scaled cross terms), then 16 epilogue warps (one thread per position) add them into a ring of four output planes in shared memory.  Along x the two
-// contributions of an output are summed in registers (warp shuffles; the two lanes at a warp seam exchange through a scratch), and
-// the taps are processed in 4 phases (kz>>1, ky>>1): within a phase a position adds one float2 (outputs 2x, 2x+1) to each of 4
-// (kz, ky) rows, different positions hit different cells, so the adds are race-free without atomics; a barrier separates phases
-// (shared-memory traffic: 1/4 of a per-tap scatter, and conflict-free).  Output planes
-// 2z-1 and 2z are complete after step z (their other contributions came from step z-1, carried in the ring) and leave with
-// 16-byte stores.  Only the two output rows on each side of a band are shared with the neighbouring band's CTA: those are
+// 2^11-scaled cross terms), then 16 epilogue warps (one thread per position) add them into a ring of four output planes in
+// shared memory.  Along x the two contributions of an output are summed in registers (warp shuffles; the two lanes at a warp
+// seam exchange through a scratch), and the taps are processed in 4 phases (kz>>1, ky>>1): within a phase a position adds one
+// float2 (outputs 2x, 2x+1) to each of 4 (kz, ky) rows and different positions hit different cells, so the adds are race-free
+// without atomics; a barrier separates phases (shared-memory traffic: 1/4 of a per-tap scatter, and conflict-free).  Output
+// planes 2z-1 and 2z are complete after step z (their other contributions came from step z-1, carried in the ring) and leave
+// with 16-byte stores.  Only the two output rows on each side of a band are shared with the neighbouring band's CTA: those are
 // added with red.global.add.v4.f32 onto zeroed rows (two commutative contributions: deterministic), zeroed by one strided
 // memset before the launch.  The bias is added by exactly one contributor of every output.
 #include <cuda_fp16.h>
